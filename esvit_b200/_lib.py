@@ -1,0 +1,92 @@
+"""ctypes binding of libesvit_b200.so (the C ABI declared in include/esvit_b200.h).
+
+There is no CPU / PyTorch fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_longlong, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libesvit_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "esvit_b200.h")
+
+ERR_BAD_ARG = 1001
+
+P, I, L, F, D = c_void_p, c_int, c_longlong, c_float, c_double
+
+# name -> argtypes (restype is always int).  Keep in sync with include/esvit_b200.h
+# (tests/test_abi.py parses the header and checks names + arity).
+SIGNATURES = {
+    "esvit_add_ln_fwd": [P, P, P, I, P, P, F, P, P, I, P, P, L, I, P],
+    "esvit_add_ln_bwd": [P, I, P, P, P, P, P, P, I, P, P, P, P, L, I, P],
+    "esvit_patch_merge_ln_fwd": [P, P, P, F, P, P, P, I, I, I, I, P],
+    "esvit_patch_merge_ln_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "esvit_token_mean_fwd": [P, P, I, I, I, P],
+    "esvit_token_mean_bwd": [P, P, P, I, I, I, P],
+    "esvit_patch_embed_fwd": [P, P, P, P, P, F, P, P, P, I, I, I, I, P],
+    "esvit_patch_embed_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "esvit_window_attn_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, F, P],
+    "esvit_window_attn_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
+    "esvit_gelu_fwd": [P, P, L, P],
+    "esvit_gelu_bwd": [P, P, P, L, P],
+    "esvit_l2norm_fwd": [P, P, P, F, L, I, P],
+    "esvit_l2norm_bwd": [P, P, P, P, L, I, P],
+    "esvit_weight_norm_fwd": [P, P, P, P, L, I, P],
+    "esvit_weight_norm_bwd": [P, P, P, P, P, P, L, I, P],
+    "esvit_row_lse": [P, P, F, P, L, I, P],
+    "esvit_dino_ce_fwd": [P, P, P, P, P, P, F, F, P, L, I, P],
+    "esvit_dino_ce_bwd": [P, P, P, P, P, P, P, P, F, F, P, L, I, P],
+    "esvit_weighted_sum": [P, P, I, P, P],
+    "esvit_colsum_workspace_rows": [],
+    "esvit_colsum": [P, L, I, P, P, P],
+    "esvit_center_ema": [P, P, F, F, I, P],
+    "esvit_normalize_rows": [P, P, L, I, F, P],
+    "esvit_region_match": [P, P, I, I, I, I, I, P, P, P],
+    "esvit_ema_multi": [P, P, P, I, D, P],
+    "esvit_clip_multi": [P, P, I, F, P, P, P],
+}
+
+_lib = None
+
+
+class EsvitKernelError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library, failing loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise EsvitKernelError(
+            f"{LIB_PATH} not found: the esvit_b200 CUDA library has not been built "
+            "(run `python -m esvit_b200.build` or `__graft_entry__.build()`); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def _cuda_error_string(code: int) -> str:
+    try:
+        import torch
+        return torch.cuda.cudart().cudaGetErrorString(code) if hasattr(torch.cuda.cudart(), "cudaGetErrorString") \
+            else f"cudaError {code}"
+    except Exception:
+        return f"cudaError {code}"
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point; non-zero status -> Python exception (the reference's error convention
+    at this boundary is Python exceptions)."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        if rc == ERR_BAD_ARG:
+            raise ValueError(f"{name}: unsupported shape / argument (ESVIT_ERR_BAD_ARG)")
+        raise EsvitKernelError(f"{name} failed: {_cuda_error_string(rc)} (status {rc})")

@@ -1,0 +1,473 @@
+"""torch.autograd.Function wrappers over the esvit_b200 C ABI (one entry point per kernel).
+
+PyTorch is used here for device memory (caching allocator), the current CUDA stream and autograd bookkeeping;
+all arithmetic of these ops happens in the hand-written sm_100a kernels.  There is no fallback path: every op
+requires CUDA tensors and the built library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _p(t: Optional[Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: Optional[Tensor], dtype, name: str) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"esvit_b200 op input `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"`{name}` must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# residual add + LayerNorm
+
+
+def _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, want_y, y_bf16):
+    T, C = x.numel() // x.shape[-1], x.shape[-1]
+    xout = torch.empty_like(x) if delta is not None else None
+    y = mean = rstd = None
+    if want_y:
+        y = torch.empty(x.shape, dtype=BF16 if y_bf16 else F32, device=x.device)
+        mean = torch.empty(T, dtype=F32, device=x.device)
+        rstd = torch.empty(T, dtype=F32, device=x.device)
+    _lib.call("esvit_add_ln_fwd", _p(x), _p(delta), _p(keep), tps, _p(gamma), _p(beta), eps, _p(xout), _p(y),
+              1 if y_bf16 else 0, _p(mean), _p(rstd), T, C, _stream())
+    return (xout if delta is not None else x), y, mean, rstd
+
+
+class AddLayerNormFn(Function):
+    """(x, delta, keep) -> (xout = x + keep*delta, y = LN(xout)).  keep: per-sample DropPath scale or None."""
+
+    @staticmethod
+    def forward(ctx, x, delta, keep, gamma, beta, eps: float, y_bf16: bool):
+        x = _chk(x, F32, "x")
+        delta = _chk(delta, BF16, "delta")
+        keep = _chk(keep, F32, "keep")
+        gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        tps = x.numel() // x.shape[-1] // x.shape[0]
+        xout, y, mean, rstd = _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, True, y_bf16)
+        ctx.save_for_backward(xout, mean, rstd, gamma, keep)
+        ctx.tps, ctx.y_bf16 = tps, y_bf16
+        return xout, y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_xout, g_y):
+        xout, mean, rstd, gamma, keep = ctx.saved_tensors
+        T, C = xout.numel() // xout.shape[-1], xout.shape[-1]
+        g_xout = _chk(g_xout, F32, "g_xout") if g_xout is not None else None
+        if g_y is not None:
+            g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
+        dx = torch.empty_like(xout)
+        ddelta = torch.empty(xout.shape, dtype=BF16, device=xout.device)
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, _p(g_xout), _p(xout), _p(mean), _p(rstd),
+                  _p(gamma), _p(keep), ctx.tps, _p(dx), _p(ddelta), _p(dgamma), _p(dbeta), T, C, _stream())
+        return dx, ddelta, None, dgamma, dbeta, None, None
+
+
+class LayerNormFn(Function):
+    """x fp32 -> y = LN(x) (bf16 or fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, y_bf16: bool):
+        x = _chk(x, F32, "x")
+        gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        _, y, mean, rstd = _add_ln_fwd(x, None, None, 1, gamma, beta, eps, True, y_bf16)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.y_bf16 = y_bf16
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_y):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        T, C = x.numel() // x.shape[-1], x.shape[-1]
+        g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
+        dx = torch.empty_like(x)
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, None, _p(x), _p(mean), _p(rstd), _p(gamma),
+                  None, 1, _p(dx), None, _p(dgamma), _p(dbeta), T, C, _stream())
+        return dx, dgamma, dbeta, None, None
+
+
+class ResidualAddFn(Function):
+    """xout = x + keep * delta (fp32 + bf16), no norm."""
+
+    @staticmethod
+    def forward(ctx, x, delta, keep):
+        x, delta, keep = _chk(x, F32, "x"), _chk(delta, BF16, "delta"), _chk(keep, F32, "keep")
+        tps = x.numel() // x.shape[-1] // x.shape[0]
+        xout, _, _, _ = _add_ln_fwd(x, delta, keep, tps, None, None, 0.0, False, False)
+        ctx.save_for_backward(keep)
+        ctx.tps = tps
+        return xout
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (keep,) = ctx.saved_tensors
+        g = _chk(g, F32, "g")
+        T, C = g.numel() // g.shape[-1], g.shape[-1]
+        ddelta = torch.empty(g.shape, dtype=BF16, device=g.device)
+        _lib.call("esvit_add_ln_bwd", None, 0, _p(g), None, None, None, None, _p(keep), ctx.tps, None, _p(ddelta),
+                  None, None, T, C, _stream())
+        return g, ddelta, None
+
+
+def add_layer_norm(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor], gamma: Tensor, beta: Tensor,
+                   eps: float, y_bf16: bool = True) -> Tuple[Tensor, Tensor]:
+    if delta is None:
+        return x, LayerNormFn.apply(x, gamma, beta, eps, y_bf16)
+    return AddLayerNormFn.apply(x, delta, keep, gamma, beta, eps, y_bf16)
+
+
+def residual_add(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor]) -> Tensor:
+    return x if delta is None else ResidualAddFn.apply(x, delta, keep)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class PatchMergeLNFn(Function):
+    """x fp32 [B, H*W, C] -> LN(2x2 gather) bf16 [B, ceil(H/2)*ceil(W/2), 4C]."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, H: int, W: int):
+        x, gamma, beta = _chk(x, F32, "x"), _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        B, L, C = x.shape
+        assert L == H * W
+        Lo = ((H + 1) // 2) * ((W + 1) // 2)
+        y = torch.empty(B, Lo, 4 * C, dtype=BF16, device=x.device)
+        mean = torch.empty(B * Lo, dtype=F32, device=x.device)
+        rstd = torch.empty(B * Lo, dtype=F32, device=x.device)
+        _lib.call("esvit_patch_merge_ln_fwd", _p(x), _p(gamma), _p(beta), eps, _p(y), _p(mean), _p(rstd), B, H, W, C,
+                  _stream())
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.hw = (H, W)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        H, W = ctx.hw
+        B, L, C = x.shape
+        g = _chk(g, BF16, "g")
+        dx = torch.empty_like(x)
+        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        _lib.call("esvit_patch_merge_ln_bwd", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma),
+                  _p(dbeta), B, H, W, C, _stream())
+        return dx, dgamma, dbeta, None, None, None
+
+
+class TokenMeanFn(Function):
+    """region fp32 [B, N, C] -> pooled [B, C]."""
+
+    @staticmethod
+    def forward(ctx, region):
+        region = _chk(region, F32, "region")
+        B, N, C = region.shape
+        pooled = torch.empty(B, C, dtype=F32, device=region.device)
+        _lib.call("esvit_token_mean_fwd", _p(region), _p(pooled), B, N, C, _stream())
+        ctx.shape = (B, N, C)
+        return pooled
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        B, N, C = ctx.shape
+        g = _chk(g, F32, "g")
+        d = torch.empty(B, N, C, dtype=F32, device=g.device)
+        _lib.call("esvit_token_mean_bwd", _p(g), None, _p(d), B, N, C, _stream())
+        return d
+
+
+class PatchEmbedFn(Function):
+    """img fp32 [B,3,H,W] -> LN(conv4x4/4) fp32 [B, (H/4)(W/4), E]."""
+
+    @staticmethod
+    def forward(ctx, img, w, bias, gamma, beta, eps: float):
+        img, w, bias = _chk(img, F32, "img"), _chk(w, F32, "w"), _chk(bias, F32, "bias")
+        gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        B, Cin, H, W = img.shape
+        E = w.shape[0]
+        if Cin != 3 or tuple(w.shape[1:]) != (3, 4, 4):
+            raise ValueError("PatchEmbed kernel supports in_chans=3, patch_size=4")
+        T = B * (H // 4) * (W // 4)
+        out = torch.empty(B, (H // 4) * (W // 4), E, dtype=F32, device=img.device)
+        mean = torch.empty(T, dtype=F32, device=img.device)
+        rstd = torch.empty(T, dtype=F32, device=img.device)
+        _lib.call("esvit_patch_embed_fwd", _p(img), _p(w), _p(bias), _p(gamma), _p(beta), eps, _p(out), _p(mean),
+                  _p(rstd), B, H, W, E, _stream())
+        ctx.save_for_backward(img, w, bias, gamma, mean, rstd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        img, w, bias, gamma, mean, rstd = ctx.saved_tensors
+        B, _, H, W = img.shape
+        E = w.shape[0]
+        g = _chk(g, F32, "g")
+        dw, db = torch.zeros_like(w), torch.zeros_like(bias)
+        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        _lib.call("esvit_patch_embed_bwd", _p(img), _p(w), _p(bias), _p(gamma), _p(mean), _p(rstd), _p(g), _p(dw),
+                  _p(db), _p(dgamma), _p(dbeta), B, H, W, E, _stream())
+        return None, dw, db, dgamma, dbeta, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+class WindowAttentionFn(Function):
+    """qkv bf16 [B, H*W, 3C] -> attention output bf16 [B, H*W, C] in token order (pad/roll/partition folded in)."""
+
+    @staticmethod
+    def forward(ctx, qkv, qkv_bias, bias_table, H: int, W: int, num_heads: int, ws: int, shift: int, scale: float):
+        qkv = _chk(qkv, BF16, "qkv")
+        qkv_bias = _chk(qkv_bias, F32, "qkv_bias")
+        bias_table = _chk(bias_table, F32, "relative_position_bias_table")
+        B, L, C3 = qkv.shape
+        C = C3 // 3
+        assert L == H * W
+        qb = qkv_bias.to(BF16)
+        nwin = B * (-(-H // ws)) * (-(-W // ws))
+        out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
+        lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
+        _lib.call("esvit_window_attn_fwd", _p(qkv), _p(qb), _p(bias_table), _p(out), _p(lse), B, H, W, C, num_heads, ws,
+                  shift, scale, _stream())
+        ctx.save_for_backward(qkv, qb, bias_table, out, lse)
+        ctx.geo = (B, H, W, C, num_heads, ws, shift, scale)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        qkv, qb, bias_table, out, lse = ctx.saved_tensors
+        B, H, W, C, nH, ws, shift, scale = ctx.geo
+        g = _chk(g, BF16, "g")
+        dqkv = torch.empty_like(qkv)
+        dtable = torch.zeros_like(bias_table)
+        dqb = torch.zeros(3 * C, dtype=F32, device=qkv.device)
+        _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(out), _p(g), _p(lse), _p(dqkv),
+                  _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
+        return dqkv, dqb, dtable, None, None, None, None, None, None
+
+
+class GeluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, BF16, "x")
+        y = torch.empty_like(x)
+        _lib.call("esvit_gelu_fwd", _p(x), _p(y), x.numel(), _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _chk(g, BF16, "g")
+        dx = torch.empty_like(x)
+        _lib.call("esvit_gelu_bwd", _p(x), _p(g), _p(dx), x.numel(), _stream())
+        return dx
+
+
+class L2NormFn(Function):
+    @staticmethod
+    def forward(ctx, x, eps: float):
+        x = _chk(x, BF16, "x")
+        R, Dm = x.numel() // x.shape[-1], x.shape[-1]
+        y = torch.empty_like(x)
+        inv = torch.empty(R, dtype=F32, device=x.device)
+        _lib.call("esvit_l2norm_fwd", _p(x), _p(y), _p(inv), eps, R, Dm, _stream())
+        ctx.save_for_backward(x, inv)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, inv = ctx.saved_tensors
+        g = _chk(g, BF16, "g")
+        R, Dm = x.numel() // x.shape[-1], x.shape[-1]
+        dx = torch.empty_like(x)
+        _lib.call("esvit_l2norm_bwd", _p(x), _p(g), _p(inv), _p(dx), R, Dm, _stream())
+        return dx, None
+
+
+class WeightNormFn(Function):
+    """(v fp32 [K,D], g fp32 [K,1]) -> w bf16 [K,D] = v * g / ||v||_row."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        v, g = _chk(v, F32, "weight_v"), _chk(g, F32, "weight_g")
+        K, Dm = v.shape
+        w = torch.empty(K, Dm, dtype=BF16, device=v.device)
+        norm = torch.empty(K, dtype=F32, device=v.device)
+        _lib.call("esvit_weight_norm_fwd", _p(v), _p(g), _p(w), _p(norm), K, Dm, _stream())
+        ctx.save_for_backward(v, g, norm)
+        return w
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gw):
+        v, g, norm = ctx.saved_tensors
+        gw = _chk(gw, BF16, "gw")
+        K, Dm = v.shape
+        dv = torch.empty_like(v)
+        dg = torch.empty_like(g) if ctx.needs_input_grad[1] else None
+        _lib.call("esvit_weight_norm_bwd", _p(v), _p(g), _p(norm), _p(gw), _p(dv), _p(dg), K, Dm, _stream())
+        return dv, dg
+
+
+# ------------------------------------------------------------------------------------------------------------
+# losses
+
+
+def row_lse(x: Tensor, center: Optional[Tensor], inv_temp: float) -> Tensor:
+    x = _chk(x, BF16, "logits")
+    R, K = x.shape
+    lse = torch.empty(R, dtype=F32, device=x.device)
+    _lib.call("esvit_row_lse", _p(x), _p(center), inv_temp, _p(lse), R, K, _stream())
+    return lse
+
+
+class DinoCEFn(Function):
+    """loss = sum_r w[r] * ( n_r * LSE(s_r / tau) - sum_j <softmax((t[trow[r,j]] - center) / temp), s_r / tau> ).
+
+    s bf16 [R,K] (grad), t bf16 [Rt,K], center fp32 [K], trow int32 [R,2], w fp32 [R]."""
+
+    @staticmethod
+    def forward(ctx, s, t, center, lse_t, trow, w, inv_temp_t: float, inv_tau_s: float):
+        s, t = _chk(s, BF16, "student logits"), _chk(t, BF16, "teacher logits")
+        center, lse_t, w = _chk(center, F32, "center"), _chk(lse_t, F32, "lse_t"), _chk(w, F32, "w")
+        trow = _chk(trow, torch.int32, "trow")
+        R, K = s.shape
+        lse_s = torch.empty(R, dtype=F32, device=s.device)
+        _lib.call("esvit_row_lse", _p(s), None, inv_tau_s, _p(lse_s), R, K, _stream())
+        row_loss = torch.empty(R, dtype=F32, device=s.device)
+        _lib.call("esvit_dino_ce_fwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), inv_temp_t, inv_tau_s,
+                  _p(row_loss), R, K, _stream())
+        loss = torch.empty((), dtype=F32, device=s.device)
+        _lib.call("esvit_weighted_sum", _p(row_loss), _p(w), R, _p(loss), _stream())
+        ctx.save_for_backward(s, t, center, lse_s, lse_t, trow, w)
+        ctx.temps = (inv_temp_t, inv_tau_s)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        s, t, center, lse_s, lse_t, trow, w = ctx.saved_tensors
+        inv_temp_t, inv_tau_s = ctx.temps
+        R, K = s.shape
+        gs = _chk(g.reshape(1).to(F32), F32, "g")
+        ds = torch.empty_like(s)
+        _lib.call("esvit_dino_ce_bwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(w), _p(gs),
+                  inv_temp_t, inv_tau_s, _p(ds), R, K, _stream())
+        return ds, None, None, None, None, None, None, None
+
+
+_colsum_ws = {}
+
+
+def colsum(t: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """fp32 column sums of a bf16 [R, K] matrix (deterministic)."""
+    t = _chk(t, BF16, "teacher logits")
+    R, K = t.shape
+    key = (t.device, K)
+    ws = _colsum_ws.get(key)
+    if ws is None:
+        rows = _lib.load().esvit_colsum_workspace_rows()
+        ws = _colsum_ws[key] = torch.empty(rows * K, dtype=F32, device=t.device)
+    if out is None:
+        out = torch.empty(K, dtype=F32, device=t.device)
+    _lib.call("esvit_colsum", _p(t), R, K, _p(ws), _p(out), _stream())
+    return out
+
+
+def center_ema_(center: Tensor, colsum_total: Tensor, rows_total: int, momentum: float) -> None:
+    assert center.is_cuda and center.dtype == F32 and center.is_contiguous()
+    _lib.call("esvit_center_ema", _p(center), _p(colsum_total), float(rows_total), momentum, center.numel(),
+              _stream())
+
+
+def normalize_rows(x: Tensor, eps: float = 1e-12) -> Tensor:
+    x = _chk(x, F32, "features")
+    y = torch.empty_like(x)
+    _lib.call("esvit_normalize_rows", _p(x), _p(y), x.shape[0], x.shape[1], eps, _stream())
+    return y
+
+
+def region_match(s_fea: Tensor, t_fea: Tensor, B: int, ncrops: int, Tg: int, Tl: int) -> Tuple[Tensor, Tensor]:
+    """Cosine arg-max of every student region token against the teacher view's tokens of the same image.
+
+    Returns (idx int64 [2, ncrops, B, Tg] with -1 in unused slots, trow int32 [Rs, 2] teacher region row per iq)."""
+    sn, tn = normalize_rows(s_fea), normalize_rows(t_fea)
+    P = sn.shape[1]
+    Rs = sn.shape[0]
+    assert Rs == B * (2 * Tg + (ncrops - 2) * Tl) and tn.shape[0] == 2 * B * Tg
+    idx = torch.full((2, ncrops, B, Tg), -1, dtype=torch.int64, device=sn.device)
+    trow = torch.empty(Rs, 2, dtype=torch.int32, device=sn.device)
+    _lib.call("esvit_region_match", _p(sn), _p(tn), B, ncrops, Tg, Tl, P, _p(idx), _p(trow), _stream())
+    return idx, trow
+
+
+# ------------------------------------------------------------------------------------------------------------
+# optimiser-side multi-tensor ops
+
+
+def _ptr_array(tensors: Sequence[Tensor]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _numel_array(tensors: Sequence[Tensor]):
+    arr = (ctypes.c_longlong * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.numel()
+    return arr
+
+
+def ema_update_(teacher: Sequence[Tensor], student: Sequence[Tensor], momentum: float) -> None:
+    """teacher = teacher * m + (1 - m) * student for every tensor pair; bit-exact with the reference loop."""
+    assert len(teacher) == len(student)
+    for k, q in zip(teacher, student):
+        if not (k.is_cuda and q.is_cuda and k.dtype == F32 and q.dtype == F32 and k.is_contiguous()
+                and q.is_contiguous() and k.numel() == q.numel()):
+            raise RuntimeError("ema_update_: fp32 contiguous CUDA tensors of equal size required")
+    _lib.call("esvit_ema_multi", _ptr_array(teacher), _ptr_array(student), _numel_array(teacher), len(teacher),
+              float(momentum), _stream())
+
+
+def clip_grads_(grads: Sequence[Tensor], clip: float) -> Tensor:
+    """Per-tensor L2 clipping in place; returns the pre-clip norms as a device tensor (no host sync)."""
+    n = len(grads)
+    dev = grads[0].device
+    for g in grads:
+        if not (g.is_cuda and g.dtype == F32 and g.is_contiguous()):
+            raise RuntimeError("clip_grads_: fp32 contiguous CUDA gradients required")
+    ws = torch.empty(n, dtype=torch.float64, device=dev)
+    norms = torch.empty(n, dtype=F32, device=dev)
+    _lib.call("esvit_clip_multi", _ptr_array(grads), _numel_array(grads), n, float(clip), _p(ws), _p(norms), _stream())
+    return norms

@@ -1,0 +1,340 @@
+"""B200-native Swin backbone behind the reference's module names, signatures and state_dict keys.
+
+Drop-in for /root/reference/models/swin_transformer.py on the pre-training path: same constructor arguments,
+same parameter / buffer names (teacher.load_state_dict(student.state_dict()) and checkpoints interchange),
+``forward(x or list_of_crops)`` returning ``head(cls)`` or the dense 4-tuple exactly as
+``SwinTransformer.forward`` (models/swin_transformer.py:713-763).
+
+Execution model (what differs from the reference):
+  * the residual stream is fp32 token-major [B, H*W, C]; every branch output is bf16;
+  * ``x = shortcut + drop_path(branch)`` is fused with the NEXT LayerNorm (ops.add_layer_norm), so a block is
+    LN -> qkv GEMM -> window-attention kernel -> proj GEMM -> add+LN -> fc1 GEMM -> GELU -> fc2 GEMM, with the
+    trailing add deferred into the following block / PatchMerging / final norm;
+  * pad, cyclic shift, window partition/reverse, the relative-position bias gather and the shift mask never
+    exist as tensors - the attention kernel derives them from (H, W, window, shift);
+  * the plain GEMMs (qkv, proj, fc1, fc2, reduction) are bf16 library GEMMs (torch.nn.functional.linear).
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+def _trunc_normal_(t: Tensor, std: float = .02) -> Tensor:
+    return nn.init.trunc_normal_(t, std=std)
+
+
+def _lin(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    """bf16 library GEMM; fp32 master weights are cast per call (autograd routes the bf16 grads back to fp32)."""
+    with torch.autocast("cuda", enabled=False):
+        return F.linear(x, w.to(BF16), None if b is None else b.to(BF16))
+
+
+class _CastCache:
+    """bf16 copies of weights shared by the resolution groups of one forward call (one cast per step)."""
+
+    def __init__(self):
+        self.d: Dict[int, Tensor] = {}
+
+    def __call__(self, p: Optional[Tensor]) -> Optional[Tensor]:
+        if p is None:
+            return None
+        k = id(p)
+        t = self.d.get(k)
+        if t is None:
+            t = self.d[k] = p.to(BF16)
+        return t
+
+
+def _lin_c(x: Tensor, lin: nn.Linear, cc: Optional[_CastCache]) -> Tensor:
+    if cc is None:
+        return _lin(x, lin.weight, lin.bias)
+    with torch.autocast("cuda", enabled=False):
+        return F.linear(x, cc(lin.weight), cc(lin.bias))
+
+
+def drop_path_keep(batch: int, drop_prob: float, training: bool, device) -> Optional[Tensor]:
+    """Per-sample stochastic-depth scale (0 or 1/keep_prob) of timm 0.3.2 DropPath; None = identity."""
+    if drop_prob == 0. or not training:
+        return None
+    keep_prob = 1.0 - drop_prob
+    r = keep_prob + torch.rand(batch, dtype=torch.float32, device=device)
+    return r.floor_().div_(keep_prob)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU or drop != 0.:
+            raise NotImplementedError("the fused path implements exact GELU and drop=0 (all EsViT Swin configs)")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
+        """x bf16 [..., C] -> bf16 [..., C]."""
+        return _lin_c(ops.GeluFn.apply(_lin_c(x, self.fc1, cc)), self.fc2, cc)
+
+
+class WindowAttention(nn.Module):
+    """W-MSA / SW-MSA with relative position bias (models/swin_transformer.py:72-152), head_dim 32."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.dim = dim
+        self.window_size = tuple(window_size)
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        if head_dim != 32 or self.window_size[0] != self.window_size[1] or attn_drop != 0. or proj_drop != 0.:
+            raise NotImplementedError("kernel supports head_dim 32, square windows, no attention dropout")
+        if not qkv_bias:
+            raise NotImplementedError("qkv_bias=False is not used by any EsViT config")
+        ws = self.window_size[0]
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) * (2 * ws - 1), num_heads))
+        t = torch.arange(ws * ws)
+        y, x = t // ws, t % ws
+        idx = (y[:, None] - y[None, :] + ws - 1) * (2 * ws - 1) + (x[:, None] - x[None, :] + ws - 1)
+        self.register_buffer("relative_position_index", idx)  # kept for state_dict parity; the kernel uses the closed form
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        _trunc_normal_(self.relative_position_bias_table, std=.02)
+
+    def attend(self, y: Tensor, H: int, W: int, shift: int, cc: Optional[_CastCache] = None) -> Tensor:
+        """y = norm1(x) bf16 [B, H*W, C] in token order -> proj(attention) bf16 [B, H*W, C]."""
+        qkv = _lin_c(y, self.qkv, cc)
+        a = ops.WindowAttentionFn.apply(qkv, self.qkv.bias, self.relative_position_bias_table, H, W, self.num_heads,
+                                        self.window_size[0], shift, float(self.scale))
+        return _lin_c(a, self.proj, cc)
+
+    def forward(self, x: Tensor, mask: Optional[Tensor] = None):
+        """Reference signature: x [num_windows*B, N, C] pre-partitioned windows.  Only mask=None is supported
+        standalone (the shifted case is handled inside SwinTransformerBlock from the geometry); the attention
+        probabilities (2nd return of the reference) are never materialised -> None."""
+        if mask is not None:
+            raise NotImplementedError("explicit masks are generated in-kernel; call SwinTransformerBlock instead")
+        ws = self.window_size[0]
+        B_, N, C = x.shape
+        assert N == ws * ws
+        return self.attend(x.to(BF16), ws, ws, 0), None
+
+
+class SwinTransformerBlock(nn.Module):
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim, self.input_resolution, self.num_heads = dim, input_resolution, num_heads
+        self.window_size, self.shift_size, self.mlp_ratio = window_size, shift_size, mlp_ratio
+        if min(self.input_resolution) <= self.window_size:  # models/swin_transformer.py:206-209
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, (self.window_size, self.window_size), num_heads, qkv_bias, qk_scale,
+                                    attn_drop, drop)
+        self.drop_prob = float(drop_path)
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def fused(self, x: Tensor, pending, cc: Optional[_CastCache] = None):
+        """(x fp32 [B,L,C], pending=(delta bf16, keep) or None) -> (x, pending) with the MLP add deferred."""
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        delta, keep = pending if pending is not None else (None, None)
+        x, y = ops.add_layer_norm(x, delta, keep, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        a = self.attn.attend(y, H, W, self.shift_size, cc)
+        k1 = drop_path_keep(B, self.drop_prob, self.training, x.device)
+        x, y = ops.add_layer_norm(x, a, k1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        z = self.mlp(y, cc)
+        k2 = drop_path_keep(B, self.drop_prob, self.training, x.device)
+        return x, (z, k2)
+
+    def forward(self, x: Tensor):
+        """Reference signature: x [B, L, C] -> (x, attn); attn probabilities are not materialised (None)."""
+        x, pend = self.fused(x.float(), None)
+        return ops.residual_add(x, *pend), None
+
+
+class PatchMerging(nn.Module):
+    def __init__(self, input_resolution, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution, self.dim = input_resolution, dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def forward(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
+        """x fp32 [B, H*W, C] -> fp32 [B, H*W/4, 2C]."""
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        y = ops.PatchMergeLNFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, H, W)
+        return _lin_c(y, self.reduction, cc).float()
+
+
+class BasicLayer(nn.Module):
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None):
+        super().__init__()
+        self.dim, self.input_resolution, self.depth = dim, input_resolution, depth
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads,
+                                 window_size=window_size, shift_size=0 if (i % 2 == 0) else window_size // 2,
+                                 mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop,
+                                 attn_drop=attn_drop,
+                                 drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
+                                 norm_layer=norm_layer) for i in range(depth)])
+        self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample else None
+
+    def fused(self, x: Tensor, cc: Optional[_CastCache] = None):
+        pend = None
+        for blk in self.blocks:
+            x, pend = blk.fused(x, pend, cc)
+        if self.downsample is not None:
+            x = ops.residual_add(x, *pend)
+            return self.downsample(x, cc), None
+        return x, pend
+
+    def forward(self, x: Tensor) -> Tensor:
+        x, pend = self.fused(x.float())
+        return x if pend is None else ops.residual_add(x, *pend)
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        img_size = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
+        patch_size = (patch_size, patch_size) if isinstance(patch_size, int) else tuple(patch_size)
+        if patch_size != (4, 4) or in_chans != 3 or norm_layer is None:
+            raise NotImplementedError("kernel supports patch_size=4, in_chans=3, patch_norm=True (all EsViT Swin configs)")
+        self.img_size, self.patch_size = img_size, patch_size
+        self.patches_resolution = [img_size[0] // 4, img_size[1] // 4]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans, self.embed_dim = in_chans, embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)  # parameter container
+        self.norm = norm_layer(embed_dim)
+
+    def forward(self, x: Tensor) -> Tensor:
+        """x fp32 [B,3,H,W] -> fp32 [B, (H/4)(W/4), E]."""
+        return ops.PatchEmbedFn.apply(x.float(), self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
+                                      self.norm.eps)
+
+
+class SwinTransformer(nn.Module):
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, num_classes=1000, embed_dim=96, depths=[2, 2, 6, 2],
+                 num_heads=[3, 6, 12, 24], window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 use_dense_prediction=False, **kwargs):
+        super().__init__()
+        if ape or drop_rate != 0. or not patch_norm:
+            raise NotImplementedError("ape / dropout / patch_norm=False are not used by any EsViT Swin config")
+        self.num_classes = num_classes
+        self.num_layers = len(depths)
+        self.embed_dim = embed_dim
+        self.ape, self.patch_norm = ape, patch_norm
+        self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+        self.mlp_ratio = mlp_ratio
+        self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim, norm_layer)
+        pr = self.patch_embed.patches_resolution
+        self.patches_resolution = pr
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            self.layers.append(BasicLayer(
+                dim=int(embed_dim * 2 ** i), input_resolution=(pr[0] // (2 ** i), pr[1] // (2 ** i)),
+                depth=depths[i], num_heads=num_heads[i], window_size=window_size, mlp_ratio=mlp_ratio,
+                qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate,
+                drop_path=dpr[sum(depths[:i]):sum(depths[:i + 1])], norm_layer=norm_layer,
+                downsample=PatchMerging if i < self.num_layers - 1 else None))
+        self.norm = norm_layer(self.num_features)
+        self.avgpool = nn.AdaptiveAvgPool1d(1)  # structural parity only; ops.TokenMeanFn does the work
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+        self.use_dense_prediction = use_dense_prediction
+        if self.use_dense_prediction:
+            self.head_dense = None
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            _trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'absolute_pos_embed'}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {'relative_position_bias_table'}
+
+    def forward_features(self, x: Tensor, cc: Optional[_CastCache] = None):
+        """models/swin_transformer.py:678-694 -> pooled fp32 [B, D] (and region fp32 [B, N, D] in dense mode)."""
+        x = self.patch_embed(x)
+        pend = None
+        for layer in self.layers:
+            x, pend = layer.fused(x, cc)
+        delta, keep = pend if pend is not None else (None, None)
+        _, x_region = ops.add_layer_norm(x, delta, keep, self.norm.weight, self.norm.bias, self.norm.eps, y_bf16=False)
+        pooled = ops.TokenMeanFn.apply(x_region)
+        if self.use_dense_prediction:
+            return pooled, x_region
+        return pooled
+
+    def forward_feature_maps(self, x: Tensor):
+        d = self.use_dense_prediction
+        self.use_dense_prediction = True
+        try:
+            return self.forward_features(x)
+        finally:
+            self.use_dense_prediction = d
+
+    def forward(self, x):
+        """Multi-crop forward (models/swin_transformer.py:713-763): consecutive same-resolution crops are
+        concatenated on the batch axis and run once; outputs are concatenated crop-major."""
+        if not isinstance(x, list):
+            x = [x]
+        cc = _CastCache()
+        groups, start = [], 0
+        for i in range(1, len(x) + 1):
+            if i == len(x) or x[i].shape[-1] != x[start].shape[-1]:
+                groups.append((start, i))
+                start = i
+        if self.use_dense_prediction:
+            cls_l, fea_l, npatch = [], [], []
+            for s, e in groups:
+                pooled, region = self.forward_features(torch.cat(x[s:e]) if e - s > 1 else x[s], cc)
+                B, N, C = region.shape
+                cls_l.append(pooled)
+                fea_l.append(region.reshape(B * N, C))
+                npatch.append(N)
+            output_cls = torch.cat(cls_l) if len(cls_l) > 1 else cls_l[0]
+            output_fea = torch.cat(fea_l) if len(fea_l) > 1 else fea_l[0]
+            return self.head(output_cls), self.head_dense(output_fea), output_fea, npatch
+        outs = [self.forward_features(torch.cat(x[s:e]) if e - s > 1 else x[s], cc) for s, e in groups]
+        return self.head(torch.cat(outs) if len(outs) > 1 else outs[0])
+
+
+def get_cls_model(config, is_teacher=False, use_dense_prediction=False, **kwargs):
+    """Same contract as models/swin_transformer.py:947-978 (yacs config in, nn.Module out)."""
+    spec = config.MODEL.SPEC
+    return SwinTransformer(
+        img_size=config.TRAIN.IMAGE_SIZE[0], in_chans=3, num_classes=config.MODEL.NUM_CLASSES,
+        patch_size=spec['PATCH_SIZE'], embed_dim=spec['DIM_EMBED'], depths=spec['DEPTHS'],
+        num_heads=spec['NUM_HEADS'], window_size=spec['WINDOW_SIZE'], mlp_ratio=spec['MLP_RATIO'],
+        qkv_bias=spec['QKV_BIAS'], drop_rate=spec['DROP_RATE'], attn_drop_rate=spec['ATTN_DROP_RATE'],
+        drop_path_rate=0.0 if is_teacher else spec['DROP_PATH_RATE'], norm_layer=partial(nn.LayerNorm, eps=1e-6),
+        ape=spec['USE_APE'], patch_norm=spec['PATCH_NORM'], use_dense_prediction=use_dense_prediction)

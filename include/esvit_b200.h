@@ -1,0 +1,123 @@
+/* esvit_b200 C ABI — the drop-in boundary of the B200-native EsViT multi-crop self-distillation step.
+ *
+ * Every entry point takes raw DEVICE pointers + sizes + a cudaStream_t (as void*), launches sm_100a kernels on
+ * that stream and returns an int status: 0 = ok, otherwise a cudaError_t value or ESVIT_ERR_BAD_ARG (1001) for an
+ * unsupported shape.  No entry point allocates, frees or synchronises; all buffers (inputs, outputs, workspaces)
+ * are owned by the caller (PyTorch's caching allocator on the host side) and must stay alive in stream order.
+ * Entry points are re-entrant and keep no mutable global state.
+ *
+ * The reference (microsoft/esvit) is pure Python/PyTorch and has no FFI of its own; each function below names the
+ * reference code it replaces (file:line relative to the reference tree).  INTEGRATION.md shows the ctypes binding
+ * and the module-level swap a maintainer would add to main_esvit.py.
+ *
+ * Conventions: "bf16" = __nv_bfloat16 bits; token-major activations [B, H*W, C] (same order as the reference);
+ * fp32 residual stream; bf16 GEMM operands.  "ACCUMULATED" outputs must be zero-filled by the caller.
+ */
+#ifndef ESVIT_B200_H
+#define ESVIT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESVIT_ERR_BAD_ARG 1001
+
+/* ---- residual add + LayerNorm ------------------------------------------------------------------------------
+ * replaces: x = shortcut + drop_path(branch); y = norm(x)      models/swin_transformer.py:329-331, :283, :687
+ * xout = x + keep[row / tokens_per_sample] * delta (delta/keep/xout may be NULL); y = LN(xout) (y may be NULL).
+ * x fp32 [T,C]; delta bf16 [T,C]; keep fp32 [B]; y bf16 or fp32 [T,C]; mean/rstd fp32 [T] (saved for backward). */
+int esvit_add_ln_fwd(const float* x, const void* delta, const float* keep, int tokens_per_sample,
+                     const float* gamma, const float* beta, float eps, float* xout, void* y, int y_is_bf16,
+                     float* mean, float* rstd, long long T, int C, void* stream);
+/* dx = dxo + LNbwd(dy); ddelta = keep * dx (bf16); dgamma/dbeta ACCUMULATED.  dy / dxo / dx / ddelta may be NULL. */
+int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo, const float* xs, const float* mean,
+                     const float* rstd, const float* gamma, const float* keep, int tokens_per_sample, float* dx,
+                     void* ddelta, float* dgamma, float* dbeta, long long T, int C, void* stream);
+
+/* ---- PatchMerging gather + LayerNorm(4C) ---------------------------------- models/swin_transformer.py:393-417
+ * x fp32 [B,H,W,C] -> y bf16 [B,ceil(H/2)*ceil(W/2),4C] (the 4C->2C reduction GEMM follows as a library GEMM). */
+int esvit_patch_merge_ln_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                             float* rstd, int B, int H, int W, int C, void* stream);
+int esvit_patch_merge_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
+                             const float* gamma, float* dx, float* dgamma, float* dbeta, int B, int H, int W, int C,
+                             void* stream);
+
+/* ---- token mean (AdaptiveAvgPool1d(1)) ------------------------------------- models/swin_transformer.py:688-689 */
+int esvit_token_mean_fwd(const float* region, float* pooled, int B, int N, int C, void* stream);
+int esvit_token_mean_bwd(const float* dpooled, const float* dregion_in, float* dregion, int B, int N, int C,
+                         void* stream);
+
+/* ---- PatchEmbed: 4x4/4 conv (3->E) + LayerNorm -------------------------------- models/swin_transformer.py:537-547
+ * img fp32 [B,3,H,W]; w fp32 [E,3,4,4]; out fp32 [B,(H/4)*(W/4),E].  bwd ACCUMULATES dw/dbias/dgamma/dbeta. */
+int esvit_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* gamma, const float* beta,
+                          float eps, float* out, float* mean, float* rstd, int B, int H, int W, int E, void* stream);
+int esvit_patch_embed_bwd(const float* img, const float* w, const float* bias, const float* gamma, const float* mean,
+                          const float* rstd, const float* dout, float* dw, float* dbias, float* dgamma, float* dbeta,
+                          int B, int H, int W, int E, void* stream);
+
+/* ---- (shifted-)window attention core ----------------------------- models/swin_transformer.py:120-152, :283-325
+ * Folds pad / roll / window_partition / rel-pos bias / -100 shift mask / softmax / PV / window_reverse / roll / crop.
+ * qkv bf16 [B,H,W,3C] ([q|k|v][head][32]); qkv_bias bf16 [3C] (value of padded slots); bias_table fp32
+ * [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32 [B*nWindows, nH, ws*ws].  ws in {7,14}; head_dim 32.
+ * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] ACCUMULATED. */
+int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, void* out, float* lse,
+                          int B, int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
+int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, const void* out,
+                          const void* dout, const float* lse, void* dqkv, float* dbias_table, float* dqkv_bias, int B,
+                          int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
+
+/* ---- GELU (exact erf), bf16 ------------------------------------------------ models/swin_transformer.py:21-37 */
+int esvit_gelu_fwd(const void* x, void* y, long long n, void* stream);
+int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream);
+
+/* ---- DINOHead pieces ------------------------------------------------------ models/vision_transformer.py:403-417
+ * l2norm: y = x / max(||x||, eps) rows (bf16); weight_norm: w(bf16) = v * g / ||v||_row (fp32 v [K,D], g [K]). */
+int esvit_l2norm_fwd(const void* x, void* y, float* inv, float eps, long long R, int D, void* stream);
+int esvit_l2norm_bwd(const void* x, const void* dy, const float* inv, void* dx, long long R, int D, void* stream);
+int esvit_weight_norm_fwd(const float* v, const float* g, void* w, float* norm, long long K, int D, void* stream);
+int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, const void* dw, float* dv, float* dg,
+                          long long K, int D, void* stream);
+
+/* ---- DINOLoss / DDINOLoss ---------------------------------------------------- main_esvit.py:620-648, :683-750
+ * row_lse: lse[r] = log sum_k exp((x[r,k] - center[k]) * inv_temp)   (center NULL for student rows).
+ * dino_ce_fwd: row_loss[r] = n_r*lse_s[r] - sum_j <softmax((t[trow[r][j]]-center)*inv_temp_t), s[r]*inv_tau_s>
+ * dino_ce_bwd: ds[r] = gscale[0]*w[r]*inv_tau_s * (n_r*softmax(s[r]*inv_tau_s) - sum_j q_j)   (bf16 out)
+ * trow int32 [R,2], -1 = no pair.  s/t bf16 [R,K]/[Rt,K], K % 8 == 0. */
+int esvit_row_lse(const void* x, const float* center, float inv_temp, float* lse, long long R, int K, void* stream);
+int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, const float* lse_s, const float* lse_t,
+                      const int* trow, float inv_temp_t, float inv_tau_s, float* row_loss, long long R, int K,
+                      void* stream);
+int esvit_dino_ce_bwd(const void* s, const void* t, const float* center, const float* lse_s, const float* lse_t,
+                      const int* trow, const float* w, const float* gscale, float inv_temp_t, float inv_tau_s, void* ds,
+                      long long R, int K, void* stream);
+int esvit_weighted_sum(const float* v, const float* w, int R, float* out, void* stream);
+
+/* ---- update_center ----------------------------------------------------------- main_esvit.py:650-660, :752-770
+ * colsum: out[k] = sum_r t[r,k] (deterministic two-stage); workspace fp32 [esvit_colsum_workspace_rows()*K].
+ * center_ema: center = center*m + (colsum/rows_total)*(1-m)   (after the caller's SUM all-reduce of colsum). */
+int esvit_colsum_workspace_rows(void);
+int esvit_colsum(const void* t, long long R, int K, float* workspace, float* out, void* stream);
+int esvit_center_ema(float* center, const float* colsum, float rows_total, float momentum, int K, void* stream);
+
+/* ---- DDINOLoss region match -------------------------------------------------------- main_esvit.py:735-736
+ * normalize_rows: y = x / max(||x||, eps), fp32 [R,P].
+ * region_match: for every student region token of every crop v != iq, the FIRST arg-max over the Tg teacher tokens
+ * of view iq (same image) of the cosine similarity.  sn fp32 [Rs,P] rows ordered (crop, image, token) with 2 global
+ * crops of Tg tokens then ncrops-2 local crops of Tl tokens; tn fp32 [2*B*Tg, P].
+ * idx_out int64 [2, ncrops, B, Tg] (slots of v == iq or i >= T_v untouched); trow int32 [Rs,2] teacher region rows. */
+int esvit_normalize_rows(const float* x, float* y, long long R, int P, float eps, void* stream);
+int esvit_region_match(const float* sn, const float* tn, int B, int ncrops, int Tg, int Tl, int P,
+                       long long* idx_out, int* trow, void* stream);
+
+/* ---- optimiser-side multi-tensor kernels (host arrays of device pointers) ----------------------------------
+ * ema_multi: teacher = teacher*m + student*(1-m), bit-exact with main_esvit.py:587-590.
+ * clip_multi: per-tensor L2 clip of utils.py:106-115; sumsq_ws double[n] workspace; norms fp32[n] or NULL. */
+int esvit_ema_multi(void* const* teacher, const void* const* student, const long long* numel, int n, double momentum,
+                    void* stream);
+int esvit_clip_multi(void* const* grads, const long long* numel, int n, float clip, double* sumsq_ws, float* norms,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESVIT_B200_H */
