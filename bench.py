@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py - multi-crop images/sec of the EsViT self-distillation training step (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+A "step" is one full training step over one synthetic batch: teacher fwd on 2 global crops, student fwd/bwd on
+2 global + 8 local crops, DDINOLoss (view + region), packed center all-reduce, per-tensor clip, AdamW, teacher EMA.
+`value` = images/s with the crops already resident in HBM; `e2e` = the same step fed from pinned HOST buffers
+(H2D of all crops + D2H of the loss inside the timed region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "multi-crop images/sec, Swin-T W7 pretrain step (2 global 224^2 + 8 local 96^2 crops, DDINOLoss V+R, K=65536)"
+WORKLOAD = "swin_tiny_w7 2+8 crops DDINOLoss out_dim=65536 (BASELINE.json configs[1])"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="esvit_b200", choices=["esvit_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--arch", default="swin_tiny_w7")
+    ap.add_argument("--out-dim", type=int, default=65536)
+    ap.add_argument("--local-crops", type=int, default=8)
+    ap.add_argument("--device", default=None, help="reference arm only: cpu (default) or cuda (eager oracle)")
+    ap.add_argument("--ref-batch", type=int, default=2, help="reference arm: images per bounded-sample step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 1 step to this path")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_crops(batch: int, n_local: int, rank: int):
+    """per-rank generator 1234+r, N(0,1) fp32 crops."""
+    g = torch.Generator().manual_seed(1234 + rank)
+    crops = [torch.randn(batch, 3, 224, 224, generator=g) for _ in range(2)]
+    crops += [torch.randn(batch, 3, 96, 96, generator=g) for _ in range(n_local)]
+    return crops
+
+
+def max_over_ranks(ms: float, device) -> float:
+    if dist.is_initialized():
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def barrier_sync():
+    if dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(arch: str, out_dim: int, n_local: int, batch: int, steps: int, warmup: int, device: str = "cpu"):
+    """The oracle port of the reference step (oracle/step.py) timed on the host cores (all threads)."""
+    from esvit_b200.engine import SWIN_SPECS
+    from oracle import step as ST
+    from oracle import swin as S
+    spec_d = SWIN_SPECS[arch]
+    spec = S.SwinSpec(img_size=224, embed_dim=spec_d["embed_dim"], depths=tuple(spec_d["depths"]),
+                      num_heads=tuple(spec_d["num_heads"]), window_size=spec_d["window_size"], use_dense_prediction=True)
+    # random-init weights of the architecture, through the product's module constructors (same init law as the reference)
+    from esvit_b200.engine import build_network
+    torch.manual_seed(0)
+    net = build_network(dict(spec_d), out_dim, True)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    del net
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = ST.OracleStep(sd, spec, 2 + n_local, out_dim, device=device)
+    crops = [c.to(device) for c in synthetic_crops(batch, n_local, 0)]
+    if device != "cpu":
+        def run(n):
+            for _ in range(n):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    orc.step(crops)
+            torch.cuda.synchronize()
+    else:
+        def run(n):
+            for _ in range(n):
+                orc.step(crops)
+    run(warmup)
+    t0 = time.perf_counter()
+    run(steps)
+    dt = (time.perf_counter() - t0) / steps
+    return dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    device = args.device or "cpu"
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if device == "cpu":
+        steps, warmup = min(steps, 5), min(warmup, 1)  # bounded sample: ~1.5 s per B=2 step on 8 cores
+        batch = args.ref_batch
+    else:
+        batch = args.batch
+    dt, cores = cpu_reference_steps(args.arch, args.out_dim, args.local_crops, batch, steps, warmup, device)
+    val = batch / dt
+    sample = f"{steps} steps of batch {batch} ({WORKLOAD}), fp32, oracle port (oracle/step.py), {cores} threads" \
+        if device == "cpu" else f"{steps} steps of batch {batch}, oracle port eager on cuda with bf16 autocast"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+           "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32" if device == "cpu" else "bf16", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "batch_per_step": batch, "device": device},
+           "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA (there is no CPU fallback of the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    from esvit_b200 import _lib, engine
+    B, n_local = args.batch, args.local_crops
+    ncrops = 2 + n_local
+    base_lr = 5e-4 * (B * world) / 256.0
+    step, student, teacher, loss_mod = engine.make_step(
+        arch=args.arch, out_dim=args.out_dim, ncrops=ncrops, dense=True, device=dev, lr=base_lr, ddp=world > 1)
+    student.train()
+    teacher.train()
+    host = [c.pin_memory() for c in synthetic_crops(B, n_local, rank)]
+    crops = [c.to(dev) for c in host]
+    wd, mom, epoch = 0.04, 0.996, 1  # epoch >= freeze_last_layer so the last layer trains (steady-state work)
+
+    def one_step(imgs):
+        return step(imgs, epoch, base_lr, wd, mom)
+
+    for _ in range(max(args.warmup, 3)):
+        l = one_step(crops)
+    torch.cuda.synchronize()
+    assert torch.isfinite(l).item(), "non-finite loss in warm-up"
+
+    # ---- timed region: K steps, device-resident inputs ---------------------------------------------------
+    K = args.steps
+    _lib.reset_counters()
+    _lib.time_entry_point("esvit_dino_ce_bwd")
+    sampler = ClockSampler(local_rank)
+    barrier_sync()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        one_step(crops)
+    e1.record()
+    barrier_sync()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = _lib.launch_count()
+    timed = _lib.timed_results()
+    _lib.time_entry_point(None)
+    ms_per_step = ms / K
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- end to end: pinned host crops -> H2D every step, loss read back every step ----------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(c.numel() * c.element_size() for c in host)
+        for _ in range(2):
+            float(one_step([c.to(dev, non_blocking=True) for c in host]))
+        barrier_sync()
+        e0.record()
+        for _ in range(K):
+            imgs = [c.to(dev, non_blocking=True) for c in host]
+            lv = float(one_step(imgs))  # D2H of the 4-byte loss + host sync, like metric_logger.update(loss=loss.item())
+        e1.record()
+        barrier_sync()
+        ms_e = max_over_ranks(e0.elapsed_time(e1), dev) / K
+        e2e = {"value": world * B / (ms_e / 1e3), "unit": "images/s", "ms_per_step": ms_e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": lv}
+
+    # ---- roofline of the dominant kernel (region-row CE backward), timed live with CUDA events ----------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    roofline = None
+    if timed:
+        # algorithmic bytes of one region-row launch: read student rows + read each paired teacher row
+        # once + write the bf16 gradient rows.  Per image: (170 + 98 + 170) rows x K x 2 B  
+        Tg, Tl = 49, 9
+        rows_s = B * (2 * Tg + n_local * Tl)
+        rows_t = B * 2 * Tg
+        big = [t for t in timed if t["rows"] == rows_s]
+        if big:
+            avg_ms = sum(t["ms"] for t in big) / len(big)
+            alg = (2 * rows_s + rows_t) * args.out_dim * 2
+            ach = alg / (avg_ms / 1e3) / 1e9
+            roofline = {"kernel": "dino_ce_bwd_kernel (region rows)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                        "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                        "launch_ms": avg_ms, "algorithmic_bytes": alg, "launches_timed": len(big)}
+
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            one_step(crops)
+            torch.cuda.synchronize()
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del step, student, teacher, loss_mod
+        torch.cuda.empty_cache()
+        dt, cores = cpu_reference_steps(args.arch, args.out_dim, n_local, args.ref_batch, 3, 1)
+        cpu_baseline = {"value": args.ref_batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"3 steps (+1 warm-up) of batch {args.ref_batch} of the same workload, fp32, "
+                                  f"oracle/step.py on {cores} host threads, {dt:.2f} s/step"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "arch": args.arch, "batch_per_gpu": B, "global_batch": B * world,
+                          "crops": f"2x224^2 + {n_local}x96^2", "out_dim": args.out_dim, "parallelism": f"dp{world}",
+                          "drop_path": "yaml (0.1)", "optimizer": "AdamW fused",
+                          "l2": "per-step working set (>10 GB of activations/logits) >> 126 MB L2; no explicit flush"},
+               "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+               "cpu_baseline": cpu_baseline, "loss": float(l)}
+        print(json.dumps(out), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

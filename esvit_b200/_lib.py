@@ -41,7 +41,7 @@ SIGNATURES = {
     "esvit_weighted_sum": [P, P, I, P, P],
     "esvit_colsum_workspace_rows": [],
     "esvit_colsum": [P, L, I, P, P, P],
-    "esvit_center_ema": [P, P, F, F, I, P],
+    "esvit_center_ema": [P, P, F, F, P, I, P],
     "esvit_normalize_rows": [P, P, L, I, F, P],
     "esvit_region_match": [P, P, I, I, I, I, I, P, P, P],
     "esvit_ema_multi": [P, P, P, I, D, P],
@@ -90,3 +90,59 @@ def call(name: str, *args) -> None:
         if rc == ERR_BAD_ARG:
             raise ValueError(f"{name}: unsupported shape / argument (ESVIT_ERR_BAD_ARG)")
         raise EsvitKernelError(f"{name} failed: {_cuda_error_string(rc)} (status {rc})")
+
+
+# ---- instrumentation used by bench.py (launch counting; live CUDA-event timing of one entry point) --------------
+# kernels launched per call of each entry point (entries that launch more than one kernel are computed per call)
+_LAUNCHES = {"esvit_colsum": 2}
+_launch_count = 0
+_timed_name = None
+_timed_events = []
+_ROWS_ARG = {"esvit_dino_ce_bwd": -3, "esvit_dino_ce_fwd": -3, "esvit_row_lse": -3}
+
+
+def reset_counters() -> None:
+    global _launch_count
+    _launch_count = 0
+    _timed_events.clear()
+
+
+def launch_count() -> int:
+    return _launch_count
+
+
+def time_entry_point(name) -> None:
+    """Bracket every call of `name` with CUDA events on the launching (current) stream."""
+    global _timed_name
+    _timed_name = name
+
+
+def timed_results():
+    """[{ms, rows}] of the timed entry point (call after a device synchronize)."""
+    out = []
+    for e0, e1, rows in _timed_events:
+        out.append({"ms": e0.elapsed_time(e1), "rows": rows})
+    return out
+
+
+_plain_call = call
+
+
+def call(name: str, *args) -> None:  # noqa: F811  (instrumented wrapper)
+    global _launch_count
+    if name == "esvit_ema_multi":
+        _launch_count += (args[3] + 63) // 64
+    elif name == "esvit_clip_multi":
+        _launch_count += 2 * ((args[2] + 63) // 64)
+    else:
+        _launch_count += _LAUNCHES.get(name, 1)
+    if name == _timed_name:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _plain_call(name, *args)
+        e1.record()
+        rows = int(args[_ROWS_ARG[name]]) if name in _ROWS_ARG else 0
+        _timed_events.append((e0, e1, rows))
+    else:
+        _plain_call(name, *args)

@@ -92,10 +92,11 @@ __global__ void __launch_bounds__(LT) dino_ce_fwd_kernel(
   const float l0 = t0 >= 0 ? lse_t[t0] : 0.f, l1 = t1 >= 0 ? lse_t[t1] : 0.f;
   float acc = 0.f;
   for (int i = threadIdx.x; i < K / 8; i += LT) {
-    float fs[8], c[8];
+    float fs[8];
     unpack8(sr[i], fs);
-    *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(center + i * 8);
-    *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(center + i * 8 + 4);
+    const float4 c0 = *reinterpret_cast<const float4*>(center + i * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(center + i * 8 + 4);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
     float q[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) q[j] = 0.f;
@@ -137,10 +138,11 @@ __global__ void __launch_bounds__(LT) dino_ce_bwd_kernel(
   const float n = (float)((t0 >= 0) + (t1 >= 0));
   const float coef = gscale[0] * w[r] * inv_tau_s, ls = lse_s[r];
   for (int i = threadIdx.x; i < K / 8; i += LT) {
-    float fs[8], c[8], g[8];
+    float fs[8], g[8];
     unpack8(sr[i], fs);
-    *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(center + i * 8);
-    *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(center + i * 8 + 4);
+    const float4 c0 = *reinterpret_cast<const float4*>(center + i * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(center + i * 8 + 4);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
     for (int j = 0; j < 8; j++) g[j] = n * __expf(fs[j] * inv_tau_s - ls);
     if (tr0) {
@@ -203,12 +205,12 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int GY, i
 }
 // center = center * m + (colsum / rows_total) * (1 - m); products/sum rounded separately like the reference's
 // three ATen ops (main_esvit.py:657-660)
-__global__ void center_ema_kernel(float* __restrict__ center, const float* __restrict__ colsum, float rows_total,
-                                  float m, float one_minus_m, int K) {
+__global__ void center_ema_kernel(const float* __restrict__ center, const float* __restrict__ colsum,
+                                  float rows_total, float m, float one_minus_m, float* __restrict__ out, int K) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const float bc = __fdiv_rn(colsum[k], rows_total);
-  center[k] = __fadd_rn(__fmul_rn(center[k], m), __fmul_rn(bc, one_minus_m));
+  out[k] = __fadd_rn(__fmul_rn(center[k], m), __fmul_rn(bc, one_minus_m));
 }
 
 // ---- region match -----------------------------------------------------------------------------
@@ -340,11 +342,12 @@ ESVIT_API int esvit_colsum(const void* t, long long R, int K, float* workspace, 
   ESVIT_LAUNCH_CHECK();
 }
 
-ESVIT_API int esvit_center_ema(float* center, const float* colsum, float rows_total, float momentum, int K,
-                               void* stream) {
+ESVIT_API int esvit_center_ema(const float* center, const float* colsum, float rows_total, float momentum,
+                               float* center_out, int K, void* stream) {
   if (K <= 0) return ESVIT_ERR_BAD_ARG;
   const float om = (float)(1.0 - (double)momentum);
-  center_ema_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(center, colsum, rows_total, momentum, om, K);
+  center_ema_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(center, colsum, rows_total, momentum, om,
+                                                                       center_out, K);
   ESVIT_LAUNCH_CHECK();
 }
 

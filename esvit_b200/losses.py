@@ -59,13 +59,15 @@ class _CenteredLoss(nn.Module):
         return t if t.dtype == BF16 else t.to(BF16)
 
     @torch.no_grad()
-    def _reduce_and_update(self, sums: torch.Tensor, rows, centers):
-        """sums fp32 [n, K] local column sums -> one SUM all-reduce -> EMA of each center (main_esvit.py:650-660)."""
+    def _reduce_and_update(self, sums: torch.Tensor, rows, names):
+        """sums fp32 [n, K] local column sums -> one SUM all-reduce -> EMA of each center (main_esvit.py:650-660).
+        The buffers are REBOUND to new tensors like the reference does: the pending backward reads the old ones."""
         world = _world()
         if world > 1:
             dist.all_reduce(sums)
-        for i, (c, r) in enumerate(zip(centers, rows)):
-            ops.center_ema_(c, sums[i], r * world, self.center_momentum)
+        for i, (name, r) in enumerate(zip(names, rows)):
+            old = getattr(self, name)
+            setattr(self, name, ops.center_ema(old.view(-1), sums[i], r * world, self.center_momentum).view_as(old))
 
 
 class DINOLoss(_CenteredLoss):
@@ -86,7 +88,7 @@ class DINOLoss(_CenteredLoss):
     @torch.no_grad()
     def update_center(self, teacher_output):
         sums = ops.colsum(self._as_bf16(teacher_output)).view(1, -1)
-        self._reduce_and_update(sums, [teacher_output.shape[0]], [self.center.view(-1)])
+        self._reduce_and_update(sums, [teacher_output.shape[0]], ["center"])
 
 
 class DDINOLoss(_CenteredLoss):
@@ -141,4 +143,4 @@ class DDINOLoss(_CenteredLoss):
         ops.colsum(self._as_bf16(teacher_output), out=sums[0])
         ops.colsum(self._as_bf16(teacher_grid_output), out=sums[1])
         self._reduce_and_update(sums, [teacher_output.shape[0], teacher_grid_output.shape[0]],
-                                [self.center.view(-1), self.center_grid.view(-1)])
+                                ["center", "center_grid"])

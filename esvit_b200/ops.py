@@ -404,10 +404,13 @@ def colsum(t: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
-def center_ema_(center: Tensor, colsum_total: Tensor, rows_total: int, momentum: float) -> None:
+def center_ema(center: Tensor, colsum_total: Tensor, rows_total: int, momentum: float) -> Tensor:
+    """Returns a NEW tensor center*m + (colsum/rows)*(1-m) (the loss backward still reads the old center)."""
     assert center.is_cuda and center.dtype == F32 and center.is_contiguous()
-    _lib.call("esvit_center_ema", _p(center), _p(colsum_total), float(rows_total), momentum, center.numel(),
+    out = torch.empty_like(center)
+    _lib.call("esvit_center_ema", _p(center), _p(colsum_total), float(rows_total), momentum, _p(out), center.numel(),
               _stream())
+    return out
 
 
 def normalize_rows(x: Tensor, eps: float = 1e-12) -> Tensor:

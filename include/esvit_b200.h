@@ -94,10 +94,12 @@ int esvit_weighted_sum(const float* v, const float* w, int R, float* out, void* 
 
 /* ---- update_center ----------------------------------------------------------- main_esvit.py:650-660, :752-770
  * colsum: out[k] = sum_r t[r,k] (deterministic two-stage); workspace fp32 [esvit_colsum_workspace_rows()*K].
- * center_ema: center = center*m + (colsum/rows_total)*(1-m)   (after the caller's SUM all-reduce of colsum). */
+ * center_ema: center_out = center*m + (colsum/rows_total)*(1-m)  (after the caller's SUM all-reduce of colsum);
+ * out-of-place like the reference's rebinding, because the loss backward still reads the old center. */
 int esvit_colsum_workspace_rows(void);
 int esvit_colsum(const void* t, long long R, int K, float* workspace, float* out, void* stream);
-int esvit_center_ema(float* center, const float* colsum, float rows_total, float momentum, int K, void* stream);
+int esvit_center_ema(const float* center, const float* colsum, float rows_total, float momentum, float* center_out,
+                     int K, void* stream);
 
 /* ---- DDINOLoss region match -------------------------------------------------------- main_esvit.py:735-736
  * normalize_rows: y = x / max(||x||, eps), fp32 [R,P].

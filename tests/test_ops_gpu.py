@@ -380,6 +380,6 @@ def test_clip_gradients_per_tensor():
     d = _dev()
     gc = [g.to(d) for g in gs]
     norms = ops.clip_grads_(gc, 3.0)
-    assert_close(norms, torch.tensor(norms_r), 1e-6, "norms")
+    assert_close(norms, torch.tensor(norms_r), 1e-5, "norms")
     for a, b in zip(gc, ref):
-        assert_close(a, b, 1e-6, "clipped grad")
+        assert_close(a, b, 1e-5, "clipped grad")
