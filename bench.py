@@ -123,6 +123,37 @@ def barrier_sync():
 
 
 # ---------------------------------------------------------------------------------------------------------
+def pick_cpu_threads(sd, spec, crops) -> int:
+    """All the host threads the reference path can USE: eager fp32 torch on many small ops collapses when
+    oversubscribed (128 threads measured 150x slower than 8-16 on the pool's hosts), so the thread count is
+    calibrated on one teacher forward among {8,16,32,64} capped by the cores this process may run on."""
+    from oracle import swin as S
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    try:  # cgroup v2 CPU quota
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            avail = max(1, min(avail, int(int(q) / int(p))))
+    except Exception:
+        pass
+    best, best_t = 1, float("inf")
+    for n in (8, 16, 32, 64):
+        if n > avail and n != 8:
+            break
+        n = min(n, avail)
+        torch.set_num_threads(n)
+        with torch.no_grad():
+            S.multicrop_forward([c[:1] for c in crops[:2]], sd, spec)  # warm
+            t0 = time.perf_counter()
+            S.multicrop_forward([c[:1] for c in crops[:2]], sd, spec)
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    return best
+
+
 def cpu_reference_steps(arch: str, out_dim: int, n_local: int, batch: int, steps: int, warmup: int, device: str = "cpu"):
     """The oracle port of the reference step (oracle/step.py) timed on the host cores (all threads)."""
     from esvit_b200.engine import SWIN_SPECS
@@ -137,10 +168,10 @@ def cpu_reference_steps(arch: str, out_dim: int, n_local: int, batch: int, steps
     net = build_network(dict(spec_d), out_dim, True)
     sd = {k: v.detach() for k, v in net.state_dict().items()}
     del net
-    cores = os.cpu_count() or 1
+    crops = [c.to(device) for c in synthetic_crops(batch, n_local, 0)]
+    cores = pick_cpu_threads(sd, spec, crops) if device == "cpu" else 1
     torch.set_num_threads(cores)
     orc = ST.OracleStep(sd, spec, 2 + n_local, out_dim, device=device)
-    crops = [c.to(device) for c in synthetic_crops(batch, n_local, 0)]
     if device != "cpu":
         def run(n):
             for _ in range(n):

@@ -8,11 +8,26 @@
 
 namespace {
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output resolution): one ex2, one rcp and
+// five FMAs instead of erff()'s ~30-instruction path - the GELU kernels are otherwise ALU-bound, not HBM-bound.
+// e = exp(-x^2/2) is shared with the Gaussian pdf of the derivative.
+__device__ __forceinline__ float erf_as(float z_abs, float e) {
+  const float t = __frcp_rn(fmaf(0.3275911f, z_abs, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return 1.f - p * t * e;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  const float e = __expf(-0.5f * x * x);
+  const float er = copysignf(erf_as(fabsf(x) * 0.70710678118654752f, e), x);
+  return 0.5f * x * (1.f + er);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float e = __expf(-0.5f * x * x);
+  const float er = copysignf(erf_as(fabsf(x) * 0.70710678118654752f, e), x);
+  return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
 }
 
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16x8* __restrict__ x, bf16x8* __restrict__ y,
@@ -38,6 +53,54 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16x8* __restrict_
     for (int j = 0; j < 8; j++) g[j] *= gelu_grad_f(f[j]);
     dx[i] = pack8(g);
   }
+}
+
+// y = gelu(x + bias[col]); x bf16 [R, N], N % 8 == 0
+__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const bf16x8* __restrict__ x, const float* __restrict__ bias,
+                                                            bf16x8* __restrict__ y, long long n8, int N8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(x[i], f);
+    const int c = (int)(i % N8) * 8;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+    f[0] = gelu_f(f[0] + b0.x); f[1] = gelu_f(f[1] + b0.y); f[2] = gelu_f(f[2] + b0.z); f[3] = gelu_f(f[3] + b0.w);
+    f[4] = gelu_f(f[4] + b1.x); f[5] = gelu_f(f[5] + b1.y); f[6] = gelu_f(f[6] + b1.z); f[7] = gelu_f(f[7] + b1.w);
+    y[i] = pack8(f);
+  }
+}
+
+// dx = dy * gelu'(x + bias); dbias[col] += sum_rows dx.  grid (ceil(N/256), GY), block (32, 8): a thread owns 8
+// columns and strides over rows; the 8 row lanes are reduced in shared memory, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ bias,
+                                                            const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                                            float* __restrict__ dbias, long long R, int N) {
+  __shared__ float sh[8][256 + 8];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + col), b1 = *reinterpret_cast<const float4*>(bias + col + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
+      float f[8], g[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + r * N + col), f);
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + r * N + col), g);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        g[j] *= gelu_grad_f(f[j] + bb[j]);
+        acc[j] += g[j];
+      }
+      *reinterpret_cast<bf16x8*>(dx + r * N + col) = pack8(g);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) sh[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  float a = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; y++) a += sh[y][tid];
+  if (blockIdx.x * 256 + tid < N) atomicAdd(&dbias[blockIdx.x * 256 + tid], a);
 }
 
 // one warp per row, D % 8 == 0, D <= 8*32*NV
@@ -188,6 +251,29 @@ ESVIT_API int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long 
   if (n % 8 != 0 || n <= 0) return ESVIT_ERR_BAD_ARG;
   gelu_bwd_kernel<<<ew_grid(n / 8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const bf16x8*)x, (const bf16x8*)dy,
                                                                               (bf16x8*)dx, n / 8);
+  ESVIT_LAUNCH_CHECK();
+}
+
+// y = gelu(x + bias) with x bf16 [R, N] (the bias add of the preceding bias-free GEMM is fused here)
+ESVIT_API int esvit_bias_gelu_fwd(const void* x, const float* bias, void* y, long long R, int N, void* stream) {
+  if (N % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
+  const long long n8 = R * N / 8;
+  bias_gelu_fwd_kernel<<<ew_grid(n8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const bf16x8*)x, bias, (bf16x8*)y, n8,
+                                                                               N / 8);
+  ESVIT_LAUNCH_CHECK();
+}
+
+// dx = dy * gelu'(x + bias) (bf16); dbias fp32 [N] ACCUMULATED (caller zero-fills)
+ESVIT_API int esvit_bias_gelu_bwd(const void* x, const float* bias, const void* dy, void* dx, float* dbias,
+                                  long long R, int N, void* stream) {
+  if (N % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
+  const int gx = (N + 255) / 256;
+  long long gy = ((long long)esvit_num_sms() * 8 + gx - 1) / gx;
+  const long long maxgy = (R + 7) / 8;
+  if (gy > maxgy) gy = maxgy;
+  if (gy < 1) gy = 1;
+  bias_gelu_bwd_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, bias, (const bf16*)dy, (bf16*)dx, dbias, R, N);
   ESVIT_LAUNCH_CHECK();
 }
 

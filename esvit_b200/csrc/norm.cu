@@ -35,10 +35,10 @@ __device__ __forceinline__ float sum4(float4 v) { return (v.x + v.y) + (v.z + v.
 // forward: xout = x + keep[b] * delta ; y = LN(xout) * gamma + beta
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
-    const float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ keep,
-    int tokens_per_sample, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-    float* __restrict__ xout, OutT* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o,
-    long long T, int C) {
+    const float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ dbias,
+    const float* __restrict__ keep, int tokens_per_sample, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, float* __restrict__ xout, OutT* __restrict__ y,
+    float* __restrict__ mean_o, float* __restrict__ rstd_o, long long T, int C) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -54,6 +54,10 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
         v[i] = Vec4IO<float>::ld(x + row * C + c);
         if (delta) {
           float4 d = Vec4IO<bf16>::ld(delta + row * C + c);
+          if (dbias) {
+            const float4 db = Vec4IO<float>::ld(dbias + c);
+            d.x += db.x; d.y += db.y; d.z += db.z; d.w += db.w;
+          }
           v[i].x += ks * d.x; v[i].y += ks * d.y; v[i].z += ks * d.z; v[i].w += ks * d.w;
           if (xout) Vec4IO<float>::st(xout + row * C + c, v[i]);
         }
@@ -96,19 +100,19 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ dxo, const float* __restrict__ xs,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
     const float* __restrict__ keep, int tokens_per_sample, float* __restrict__ dx, bf16* __restrict__ ddelta,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, long long T, int C) {
-  extern __shared__ float sred[];  // [2*C]
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ ddbias, long long T, int C) {
+  extern __shared__ float sred[];  // [3*C]
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float invC = 1.f / (float)C;
-  float4 ag[NV], ab[NV];
+  float4 ag[NV], ab[NV], ad[NV];
 #pragma unroll
-  for (int i = 0; i < NV; i++) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
-  if (dy) {
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
-    __syncthreads();
+  for (int i = 0; i < NV; i++) {
+    ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ad[i] = make_float4(0, 0, 0, 0);
   }
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
   for (long long row = warp; row < T; row += nwarps) {
     const float ks = keep ? keep[row / tokens_per_sample] : 1.f;
     float4 G[NV];
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(
         if (dx) Vec4IO<float>::st(dx + row * C + c, G[i]);
         if (ddelta)
           Vec4IO<bf16>::st(ddelta + row * C + c, make_float4(ks * G[i].x, ks * G[i].y, ks * G[i].z, ks * G[i].w));
+        ad[i].x += ks * G[i].x; ad[i].y += ks * G[i].y; ad[i].z += ks * G[i].z; ad[i].w += ks * G[i].w;
       }
     }
   }
@@ -172,11 +177,24 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(
         atomicAdd(&sred[C + c + 2], ab[i].z); atomicAdd(&sred[C + c + 3], ab[i].w);
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+  }
+  if (ddbias) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        atomicAdd(&sred[2 * C + c + 0], ad[i].x); atomicAdd(&sred[2 * C + c + 1], ad[i].y);
+        atomicAdd(&sred[2 * C + c + 2], ad[i].z); atomicAdd(&sred[2 * C + c + 3], ad[i].w);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (dy) {
       atomicAdd(&dgamma[i], sred[i]);
       atomicAdd(&dbeta[i], sred[C + i]);
     }
+    if (ddbias) atomicAdd(&ddbias[i], sred[2 * C + i]);
   }
 }
 
@@ -348,19 +366,21 @@ int row_grid(long long T, int warps_per_block, int waves) {
   else if ((C_) <= 2048) { CALL(16) }          \
   else return ESVIT_ERR_BAD_ARG;
 
-ESVIT_API int esvit_add_ln_fwd(const float* x, const void* delta, const float* keep, int tokens_per_sample,
-                               const float* gamma, const float* beta, float eps, float* xout, void* y,
-                               int y_is_bf16, float* mean, float* rstd, long long T, int C, void* stream) {
+ESVIT_API int esvit_add_ln_fwd(const float* x, const void* delta, const float* delta_bias, const float* keep,
+                               int tokens_per_sample, const float* gamma, const float* beta, float eps, float* xout,
+                               void* y, int y_is_bf16, float* mean, float* rstd, long long T, int C, void* stream) {
   if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = row_grid(T, 8, 8);
 #define CALL(NV)                                                                                              \
   if (y_is_bf16)                                                                                              \
-    add_ln_fwd_kernel<NV, bf16><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep, tokens_per_sample, gamma,  \
-                                                      beta, eps, xout, (bf16*)y, mean, rstd, T, C);           \
+    add_ln_fwd_kernel<NV, bf16><<<grid, 256, 0, st>>>(x, (const bf16*)delta, delta_bias, keep,                \
+                                                      tokens_per_sample, gamma, beta, eps, xout, (bf16*)y,    \
+                                                      mean, rstd, T, C);                                      \
   else                                                                                                        \
-    add_ln_fwd_kernel<NV, float><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep, tokens_per_sample, gamma, \
-                                                       beta, eps, xout, (float*)y, mean, rstd, T, C);
+    add_ln_fwd_kernel<NV, float><<<grid, 256, 0, st>>>(x, (const bf16*)delta, delta_bias, keep,               \
+                                                       tokens_per_sample, gamma, beta, eps, xout, (float*)y,  \
+                                                       mean, rstd, T, C);
   DISPATCH_NV(C, CALL)
 #undef CALL
   ESVIT_LAUNCH_CHECK();
@@ -368,19 +388,19 @@ ESVIT_API int esvit_add_ln_fwd(const float* x, const void* delta, const float* k
 
 ESVIT_API int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo, const float* xs, const float* mean,
                                const float* rstd, const float* gamma, const float* keep, int tokens_per_sample,
-                               float* dx, void* ddelta, float* dgamma, float* dbeta, long long T, int C,
-                               void* stream) {
+                               float* dx, void* ddelta, float* dgamma, float* dbeta, float* ddelta_bias, long long T,
+                               int C, void* stream) {
   if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = row_grid(T, 8, 4);
-  const size_t smem = 2 * (size_t)C * sizeof(float);
+  const size_t smem = 3 * (size_t)C * sizeof(float);
 #define CALL(NV)                                                                                               \
   if (dy_is_bf16)                                                                                              \
     add_ln_bwd_kernel<NV, bf16><<<grid, 256, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,    \
-                                                         tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, T, C); \
+                                                         tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C); \
   else                                                                                                         \
     add_ln_bwd_kernel<NV, float><<<grid, 256, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma, keep,  \
-                                                          tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, T, C);
+                                                          tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C);
   DISPATCH_NV(C, CALL)
 #undef CALL
   ESVIT_LAUNCH_CHECK();

@@ -73,22 +73,52 @@ struct Cfg {
   static constexpr int NB = (2 * WS - 1) * (2 * WS - 1);
 };
 
-// gather the q/k/v (and optionally dO, with D = rowsum(dO * O)) rows of one (window, head) into smem
+// gather the q/k/v rows of one (window, head) into smem, adding the qkv bias on the way (the qkv GEMM is bias-free;
+// a padded slot holds the bias alone because the reference zero-pads the normalised activations, :287-290).
+// qbs: this head's bias, fp32 [3][32].
 template <int WS, int NTHREADS>
-__device__ __forceinline__ void load_qkv(const Geo& g, const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias,
-                                         int h, const int* tok, bf16* Qs, bf16* Ks, bf16* Vs) {
+__device__ __forceinline__ void load_qkv(const Geo& g, const bf16* __restrict__ qkv, const float* qbs, int h,
+                                         const int* tok, bf16* Qs, bf16* Ks, bf16* Vs) {
   using C = Cfg<WS>;
   for (int id = threadIdx.x; id < C::KP * 12; id += NTHREADS) {
     const int t = id / 12, rem = id - t * 12, part = rem >> 2, c16 = rem & 3;
-    uint4 val = make_uint4(0, 0, 0, 0);
+    bf16x8 val;
     if (t < C::NT) {
+      float f[8];
       const int tk = tok[t];
-      const bf16* src = tk >= 0 ? qkv + (long long)tk * 3 * g.C + part * g.C + h * HD + c16 * 8
-                                : qkv_bias + part * g.C + h * HD + c16 * 8;
-      val = *reinterpret_cast<const uint4*>(src);
+      if (tk >= 0) {
+        unpack8(*reinterpret_cast<const bf16x8*>(qkv + (long long)tk * 3 * g.C + part * g.C + h * HD + c16 * 8), f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = 0.f;
+      }
+      const float* bb = qbs + part * HD + c16 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] += bb[j];
+      val = pack8(f);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      val = *reinterpret_cast<const bf16x8*>(&z);
     }
     bf16* dst = (part == 0 ? Qs : (part == 1 ? Ks : Vs)) + t * LD + c16 * 8;
-    *reinterpret_cast<uint4*>(dst) = val;
+    *reinterpret_cast<bf16x8*>(dst) = val;
+  }
+}
+
+// column sums of a 16 x 32 fp32 accumulator tile (4 d-tiles x C-fragment) added to dst[32] in shared memory
+__device__ __forceinline__ void colsum_to_smem(const float (&t)[4][4], float scale, float* dst, int lane) {
+#pragma unroll
+  for (int dt = 0; dt < 4; dt++) {
+    float c0 = (t[dt][0] + t[dt][2]) * scale, c1 = (t[dt][1] + t[dt][3]) * scale;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    }
+    if (lane < 4) {
+      atomicAdd(&dst[dt * 8 + lane * 2], c0);
+      atomicAdd(&dst[dt * 8 + lane * 2 + 1], c1);
+    }
   }
 }
 
@@ -101,7 +131,7 @@ __device__ __forceinline__ int bias_index(int i, int j) {
 // ------------------------------------------------------------------------------------------------
 template <int WS>
 __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_fwd_kernel(
-    const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bias_table,
+    const bf16* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias_table,
     bf16* __restrict__ out, float* __restrict__ lse, Geo g, float scale) {
   using C = Cfg<WS>;
   constexpr int NTHREADS = C::NW * 32;
@@ -110,7 +140,8 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_fwd_kernel(
   bf16* Ks = Qs + C::KP * LD;
   bf16* Vs = Ks + C::KP * LD;
   float* bt = reinterpret_cast<float*>(Vs + C::KP * LD);
-  int* tok = reinterpret_cast<int*>(bt + C::NB);
+  float* qbs = bt + C::NB;
+  int* tok = reinterpret_cast<int*>(qbs + 3 * HD);
   int* rid = tok + C::KP;
 
   const int win = blockIdx.x, h = blockIdx.y;
@@ -124,8 +155,9 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_fwd_kernel(
     rid[i] = r;
   }
   for (int i = threadIdx.x; i < C::NB; i += NTHREADS) bt[i] = bias_table[i * g.nH + h];
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
   __syncthreads();
-  load_qkv<WS, NTHREADS>(g, qkv, qkv_bias, h, tok, Qs, Ks, Vs);
+  load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
   __syncthreads();
 
   for (int mt = warp; mt < C::MT; mt += C::NW) {
@@ -229,7 +261,7 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_fwd_kernel(
 // with one global atomic per bin per CTA.
 template <int WS>
 __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
-    const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bias_table,
+    const bf16* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias_table,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
     int nwin_total) {
@@ -245,8 +277,9 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
   bf16* dSs = Ps + C::KP * PLD;      // [KP][PLD]  dS chunk
   float* bt = reinterpret_cast<float*>(dSs + C::KP * PLD);
   float* dbt = bt + C::NB;           // rel-pos bias grad bins (this head)
-  float* dqb = dbt + C::NB;          // [3][32] padded-slot q/k/v grads (this head)
-  float* Dsm = dqb + 3 * HD;         // [KP] rowsum(dO * O)
+  float* dqb = dbt + C::NB;          // [3][32] qkv-bias grads of this head (column sums of dq / dk / dv)
+  float* qbs = dqb + 3 * HD;         // [3][32] qkv bias of this head
+  float* Dsm = qbs + 3 * HD;         // [KP] rowsum(dO * O)
   float* Lsm = Dsm + C::KP;          // [KP] lse
   int* tok = reinterpret_cast<int*>(Lsm + C::KP);
   int* rid = tok + C::KP;
@@ -257,7 +290,10 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
     bt[i] = bias_table[i * g.nH + h];
     dbt[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) dqb[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) {
+    dqb[i] = 0.f;
+    qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
+  }
 
   for (int win = blockIdx.x; win < nwin_total; win += gridDim.x) {
     const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, b = win / (g.nWx * g.nWy);
@@ -270,7 +306,7 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
       Lsm[i] = i < C::NT ? lse[((long long)win * g.nH + h) * C::NT + i] : 0.f;
     }
     __syncthreads();
-    load_qkv<WS, NTHREADS>(g, qkv, qkv_bias, h, tok, Qs, Ks, Vs);
+    load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
     // dO rows (zero for padded slots: their outputs are cropped) and D = rowsum(dO * O)
     for (int id = threadIdx.x; id < C::KP * 4; id += NTHREADS) {
       const int t = id >> 2, c16 = id & 3;
@@ -414,28 +450,22 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
         }
         const int kA = key0 + (lane >> 2), kB = kA + 8;
         const int tA = kA < C::NT ? tok[kA] : -1, tB = kB < C::NT ? tok[kB] : -1;
-        const bool padA = kA < C::NT && tA < 0, padB = kB < C::NT && tB < 0;
 #pragma unroll
         for (int dt = 0; dt < 4; dt++) {
-          const int dl = dt * 8 + (lane & 3) * 2;
-          const int d = h * HD + dl;
+          const int d = h * HD + dt * 8 + (lane & 3) * 2;
           if (tA >= 0) {
             bf16* base = dqkv + (long long)tA * 3 * g.C + d;
             *reinterpret_cast<uint32_t*>(base + g.C) = pack_bf162(dk[dt][0] * scale, dk[dt][1] * scale);
             *reinterpret_cast<uint32_t*>(base + 2 * g.C) = pack_bf162(dv[dt][0], dv[dt][1]);
-          } else if (padA) {
-            atomicAdd(&dqb[HD + dl], dk[dt][0] * scale); atomicAdd(&dqb[HD + dl + 1], dk[dt][1] * scale);
-            atomicAdd(&dqb[2 * HD + dl], dv[dt][0]); atomicAdd(&dqb[2 * HD + dl + 1], dv[dt][1]);
           }
           if (tB >= 0) {
             bf16* base = dqkv + (long long)tB * 3 * g.C + d;
             *reinterpret_cast<uint32_t*>(base + g.C) = pack_bf162(dk[dt][2] * scale, dk[dt][3] * scale);
             *reinterpret_cast<uint32_t*>(base + 2 * g.C) = pack_bf162(dv[dt][2], dv[dt][3]);
-          } else if (padB) {
-            atomicAdd(&dqb[HD + dl], dk[dt][2] * scale); atomicAdd(&dqb[HD + dl + 1], dk[dt][3] * scale);
-            atomicAdd(&dqb[2 * HD + dl], dv[dt][2]); atomicAdd(&dqb[2 * HD + dl + 1], dv[dt][3]);
           }
         }
+        colsum_to_smem(dk, scale, dqb + HD, lane);
+        colsum_to_smem(dv, 1.f, dqb + 2 * HD, lane);
       }
       if (ch + 1 < NCH) __syncthreads();  // P/dS chunk tiles are rewritten by the next chunk
     }
@@ -446,24 +476,17 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
       if (mt < C::MT) {
         const int rA = mt * 16 + (lane >> 2), rB = rA + 8;
         const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
-        const bool padA = rA < C::NT && tA < 0, padB = rB < C::NT && tB < 0;
 #pragma unroll
         for (int dt = 0; dt < 4; dt++) {
-          const int dl = dt * 8 + (lane & 3) * 2;
-          const int d = h * HD + dl;
+          const int d = h * HD + dt * 8 + (lane & 3) * 2;
           if (tA >= 0)
             *reinterpret_cast<uint32_t*>(dqkv + (long long)tA * 3 * g.C + d) =
                 pack_bf162(dq[a][dt][0] * scale, dq[a][dt][1] * scale);
-          else if (padA) {
-            atomicAdd(&dqb[dl], dq[a][dt][0] * scale); atomicAdd(&dqb[dl + 1], dq[a][dt][1] * scale);
-          }
           if (tB >= 0)
             *reinterpret_cast<uint32_t*>(dqkv + (long long)tB * 3 * g.C + d) =
                 pack_bf162(dq[a][dt][2] * scale, dq[a][dt][3] * scale);
-          else if (padB) {
-            atomicAdd(&dqb[dl], dq[a][dt][2] * scale); atomicAdd(&dqb[dl + 1], dq[a][dt][3] * scale);
-          }
         }
+        colsum_to_smem(dq[a], scale, dqb, lane);
       }
     }
   }
@@ -473,15 +496,276 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
     atomicAdd(&dqkv_bias[(i / HD) * g.C + h * HD + (i % HD)], dqb[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, ws = 7 fast path (KP = 64, one CTA = 4 warps = one (window, head) at a time, persistent over windows).
+// No shared-memory transposition and no atomics in the inner loop:
+//   phase A  warp = 16-query tile : S, P, dP, dS  -> dQ = dS K ;  dS is also summed into register accumulators
+//                                   (this warp's queries x all keys) that become the rel-pos-bias gradient
+//   phase B  warp = 16-key tile   : S^T = K Q^T, P^T, dP^T = V dO^T, dS^T recomputed in the transposed layout
+//                                   -> dV = P^T dO, dK = dS^T Q straight from the accumulator fragments
+// Only two __syncthreads per window (smem tile reuse); dqkv-bias gradients are column sums of dQ/dK/dV.
+__global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
+    const bf16* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias_table,
+    const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+    bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
+    int nwin_total) {
+  constexpr int WS = 7;
+  using C = Cfg<WS>;
+  constexpr int NTHREADS = 128;
+  static_assert(C::KP == 64 && C::NW == 4, "fast path assumes a 64-slot window and 4 warps");
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + C::KP * LD;
+  bf16* Vs = Ks + C::KP * LD;
+  bf16* dOs = Vs + C::KP * LD;
+  float* bt = reinterpret_cast<float*>(dOs + C::KP * LD);
+  float* dbt = bt + C::NB;
+  float* dqb = dbt + C::NB;
+  float* qbs = dqb + 3 * HD;
+  float* Dsm = qbs + 3 * HD;
+  float* Lsm = Dsm + C::KP;
+  int* tok = reinterpret_cast<int*>(Lsm + C::KP);
+  int* rid = tok + C::KP;
+
+  const int h = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < C::NB; i += NTHREADS) {
+    bt[i] = bias_table[i * g.nH + h];
+    dbt[i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) {
+    dqb[i] = 0.f;
+    qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
+  }
+  float dsacc[C::NT8][4];
+#pragma unroll
+  for (int nt = 0; nt < C::NT8; nt++) dsacc[nt][0] = dsacc[nt][1] = dsacc[nt][2] = dsacc[nt][3] = 0.f;
+
+  const int r0 = warp * 16;                       // this warp's query tile (phase A) / key tile (phase B)
+  const int rA = r0 + (lane >> 2), rB = rA + 8;
+  const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;  // A-fragment rows of the tile
+
+  for (int win = blockIdx.x; win < nwin_total; win += gridDim.x) {
+    const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, b = win / (g.nWx * g.nWy);
+    __syncthreads();
+    if (threadIdx.x < C::KP) {
+      const int i = threadIdx.x;
+      int t = -1, r = 0;
+      if (i < C::NT) slot_info<WS>(g, b, wy, wx, i, t, r);
+      tok[i] = t;
+      rid[i] = r;
+      Lsm[i] = i < C::NT ? lse[((long long)win * g.nH + h) * C::NT + i] : 0.f;
+    }
+    __syncthreads();
+    load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
+    for (int id = threadIdx.x; id < C::KP * 4; id += NTHREADS) {
+      const int t = id >> 2, c16 = id & 3;
+      uint4 dv = make_uint4(0, 0, 0, 0);
+      float part = 0.f;
+      const int tk = t < C::NT ? tok[t] : -1;
+      if (tk >= 0) {
+        dv = *reinterpret_cast<const uint4*>(dout + (long long)tk * g.C + h * HD + c16 * 8);
+        const uint4 ov = *reinterpret_cast<const uint4*>(out + (long long)tk * g.C + h * HD + c16 * 8);
+        float fd[8], fo[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(&dv), fd);
+        unpack8(*reinterpret_cast<const bf16x8*>(&ov), fo);
+#pragma unroll
+        for (int j = 0; j < 8; j++) part += fd[j] * fo[j];
+      }
+      *reinterpret_cast<uint4*>(dOs + t * LD + c16 * 8) = dv;
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      if (c16 == 0) Dsm[t] = part;
+    }
+    __syncthreads();
+
+    const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
+    const int ridA = rid[rA], ridB = rid[rB];
+    // ---------------- phase A: rows = queries ----------------
+    {
+      uint32_t qa[2][4], da[2][4];
+      ldsm_x4(qa[0], Qs + frag_off);
+      ldsm_x4(qa[1], Qs + frag_off + 16);
+      ldsm_x4(da[0], dOs + frag_off);
+      ldsm_x4(da[1], dOs + frag_off + 16);
+      const float lA = Lsm[rA], lB = Lsm[rB], DA = Dsm[rA], DB = Dsm[rB];
+      float dq[4][4];
+#pragma unroll
+      for (int dt = 0; dt < 4; dt++) dq[dt][0] = dq[dt][1] = dq[dt][2] = dq[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        float ds2[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          const int nt = 2 * kk + hf;
+          float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+          ds2[hf][0] = ds2[hf][1] = ds2[hf][2] = ds2[hf][3] = 0.f;
+          uint32_t kb[4];
+          const int boff = (nt * 8 + (lane & 7)) * LD + (lane >> 3) * 8;
+          ldsm_x4(kb, Ks + boff);
+          mma16816(sacc, qa[0], kb[0], kb[1]);
+          mma16816(sacc, qa[1], kb[2], kb[3]);
+          ldsm_x4(kb, Vs + boff);
+          mma16816(ds2[hf], da[0], kb[0], kb[1]);
+          mma16816(ds2[hf], da[1], kb[2], kb[3]);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int row = (e < 2) ? rA : rB;
+            const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
+            float dsv = 0.f;
+            if (col < C::NT && row < C::NT) {
+              float sv = sacc[e] * scale + bt[bias_index<WS>(row, col)];
+              if (g.shift > 0 && ((e < 2) ? ridA : ridB) != rid[col]) sv += -100.f;
+              const float pv = __expf(sv - ((e < 2) ? lA : lB));
+              dsv = pv * (ds2[hf][e] - ((e < 2) ? DA : DB));
+            }
+            ds2[hf][e] = dsv;
+            dsacc[nt][e] += dsv;
+          }
+        }
+        uint32_t sa[4];
+        sa[0] = pack_bf162(ds2[0][0], ds2[0][1]);
+        sa[1] = pack_bf162(ds2[0][2], ds2[0][3]);
+        sa[2] = pack_bf162(ds2[1][0], ds2[1][1]);
+        sa[3] = pack_bf162(ds2[1][2], ds2[1][3]);
+        const bf16* kp = Ks + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
+        uint32_t kb[4];
+        ldsm_x4_t(kb, kp);
+        mma16816(dq[0], sa, kb[0], kb[1]);
+        mma16816(dq[1], sa, kb[2], kb[3]);
+        ldsm_x4_t(kb, kp + 16);
+        mma16816(dq[2], sa, kb[0], kb[1]);
+        mma16816(dq[3], sa, kb[2], kb[3]);
+      }
+#pragma unroll
+      for (int dt = 0; dt < 4; dt++) {
+        const int d = h * HD + dt * 8 + (lane & 3) * 2;
+        if (tA >= 0)
+          *reinterpret_cast<uint32_t*>(dqkv + (long long)tA * 3 * g.C + d) = pack_bf162(dq[dt][0] * scale, dq[dt][1] * scale);
+        if (tB >= 0)
+          *reinterpret_cast<uint32_t*>(dqkv + (long long)tB * 3 * g.C + d) = pack_bf162(dq[dt][2] * scale, dq[dt][3] * scale);
+      }
+      colsum_to_smem(dq, scale, dqb, lane);
+    }
+    // ---------------- phase B: rows = keys (transposed recompute) ----------------
+    {
+      uint32_t ka[2][4], va[2][4];
+      ldsm_x4(ka[0], Ks + frag_off);
+      ldsm_x4(ka[1], Ks + frag_off + 16);
+      ldsm_x4(va[0], Vs + frag_off);
+      ldsm_x4(va[1], Vs + frag_off + 16);
+      float dv[4][4], dk[4][4];
+#pragma unroll
+      for (int dt = 0; dt < 4; dt++) {
+        dv[dt][0] = dv[dt][1] = dv[dt][2] = dv[dt][3] = 0.f;
+        dk[dt][0] = dk[dt][1] = dk[dt][2] = dk[dt][3] = 0.f;
+      }
+#pragma unroll
+      for (int qq = 0; qq < 4; qq++) {
+        float pT[2][4], dsT[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          const int nt = 2 * qq + hf;  // 8-query tile
+          pT[hf][0] = pT[hf][1] = pT[hf][2] = pT[hf][3] = 0.f;
+          dsT[hf][0] = dsT[hf][1] = dsT[hf][2] = dsT[hf][3] = 0.f;
+          uint32_t qb[4];
+          const int boff = (nt * 8 + (lane & 7)) * LD + (lane >> 3) * 8;
+          ldsm_x4(qb, Qs + boff);
+          mma16816(pT[hf], ka[0], qb[0], qb[1]);
+          mma16816(pT[hf], ka[1], qb[2], qb[3]);
+          ldsm_x4(qb, dOs + boff);
+          mma16816(dsT[hf], va[0], qb[0], qb[1]);
+          mma16816(dsT[hf], va[1], qb[2], qb[3]);
+          const int q0 = nt * 8 + (lane & 3) * 2;
+          const float2 lq = *reinterpret_cast<const float2*>(Lsm + q0);
+          const float2 Dq = *reinterpret_cast<const float2*>(Dsm + q0);
+          const int2 rq = *reinterpret_cast<const int2*>(rid + q0);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int key = (e < 2) ? rA : rB;
+            const int qry = q0 + (e & 1);
+            float pv = 0.f, dsv = 0.f;
+            if (key < C::NT && qry < C::NT) {
+              float sv = pT[hf][e] * scale + bt[bias_index<WS>(qry, key)];
+              if (g.shift > 0 && ((e < 2) ? ridA : ridB) != ((e & 1) ? rq.y : rq.x)) sv += -100.f;
+              pv = __expf(sv - ((e & 1) ? lq.y : lq.x));
+              dsv = pv * (dsT[hf][e] - ((e & 1) ? Dq.y : Dq.x));
+            }
+            pT[hf][e] = pv;
+            dsT[hf][e] = dsv;
+          }
+        }
+        uint32_t pa[4], sa[4];
+        pa[0] = pack_bf162(pT[0][0], pT[0][1]);
+        pa[1] = pack_bf162(pT[0][2], pT[0][3]);
+        pa[2] = pack_bf162(pT[1][0], pT[1][1]);
+        pa[3] = pack_bf162(pT[1][2], pT[1][3]);
+        sa[0] = pack_bf162(dsT[0][0], dsT[0][1]);
+        sa[1] = pack_bf162(dsT[0][2], dsT[0][3]);
+        sa[2] = pack_bf162(dsT[1][0], dsT[1][1]);
+        sa[3] = pack_bf162(dsT[1][2], dsT[1][3]);
+        const int toff = (qq * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
+        uint32_t bb[4];
+        ldsm_x4_t(bb, dOs + toff);
+        mma16816(dv[0], pa, bb[0], bb[1]);
+        mma16816(dv[1], pa, bb[2], bb[3]);
+        ldsm_x4_t(bb, dOs + toff + 16);
+        mma16816(dv[2], pa, bb[0], bb[1]);
+        mma16816(dv[3], pa, bb[2], bb[3]);
+        ldsm_x4_t(bb, Qs + toff);
+        mma16816(dk[0], sa, bb[0], bb[1]);
+        mma16816(dk[1], sa, bb[2], bb[3]);
+        ldsm_x4_t(bb, Qs + toff + 16);
+        mma16816(dk[2], sa, bb[0], bb[1]);
+        mma16816(dk[3], sa, bb[2], bb[3]);
+      }
+#pragma unroll
+      for (int dt = 0; dt < 4; dt++) {
+        const int d = h * HD + dt * 8 + (lane & 3) * 2;
+        if (tA >= 0) {
+          bf16* base = dqkv + (long long)tA * 3 * g.C + d;
+          *reinterpret_cast<uint32_t*>(base + g.C) = pack_bf162(dk[dt][0] * scale, dk[dt][1] * scale);
+          *reinterpret_cast<uint32_t*>(base + 2 * g.C) = pack_bf162(dv[dt][0], dv[dt][1]);
+        }
+        if (tB >= 0) {
+          bf16* base = dqkv + (long long)tB * 3 * g.C + d;
+          *reinterpret_cast<uint32_t*>(base + g.C) = pack_bf162(dk[dt][2] * scale, dk[dt][3] * scale);
+          *reinterpret_cast<uint32_t*>(base + 2 * g.C) = pack_bf162(dv[dt][2], dv[dt][3]);
+        }
+      }
+      colsum_to_smem(dk, scale, dqb + HD, lane);
+      colsum_to_smem(dv, 1.f, dqb + 2 * HD, lane);
+    }
+  }
+  // flush the register-resident rel-pos-bias gradient of this warp's query rows
+#pragma unroll
+  for (int nt = 0; nt < C::NT8; nt++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int row = (e < 2) ? rA : rB;
+      const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
+      if (row < C::NT && col < C::NT) atomicAdd(&dbt[bias_index<WS>(row, col)], dsacc[nt][e]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C::NB; i += NTHREADS) atomicAdd(&dbias_table[i * g.nH + h], dbt[i]);
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS)
+    atomicAdd(&dqkv_bias[(i / HD) * g.C + h * HD + (i % HD)], dqb[i]);
+}
+
+static size_t bwd7_smem() {
+  using C = Cfg<7>;
+  return (size_t)4 * C::KP * LD * 2 + (size_t)(2 * C::NB + 6 * HD + 2 * C::KP) * 4 + (size_t)2 * C::KP * 4;
+}
+
 template <int WS>
 size_t fwd_smem() {
   using C = Cfg<WS>;
-  return (size_t)3 * C::KP * LD * 2 + (size_t)C::NB * 4 + (size_t)2 * C::KP * 4;
+  return (size_t)3 * C::KP * LD * 2 + (size_t)(C::NB + 3 * HD) * 4 + (size_t)2 * C::KP * 4;
 }
 template <int WS>
 size_t bwd_smem() {
   using C = Cfg<WS>;
-  return (size_t)4 * C::KP * LD * 2 + (size_t)2 * C::KP * PLD * 2 + (size_t)(2 * C::NB + 3 * HD + 2 * C::KP) * 4 +
+  return (size_t)4 * C::KP * LD * 2 + (size_t)2 * C::KP * PLD * 2 + (size_t)(2 * C::NB + 6 * HD + 2 * C::KP) * 4 +
          (size_t)2 * C::KP * 4;
 }
 
@@ -497,8 +781,8 @@ static bool make_geo(Geo& g, int B, int H, int W, int C, int nH, int ws, int shi
 
 }  // namespace wa
 
-// qkv bf16 [B,H,W,3C] (channel order [q|k|v][head][32]); qkv_bias bf16 [3C]; bias_table fp32 [(2ws-1)^2, nH];
-// out bf16 [B,H,W,C]; lse fp32 [B*nW, nH, ws*ws]
+// qkv bf16 [B,H,W,3C] = bias-free qkv GEMM output (channel order [q|k|v][head][32]); qkv_bias fp32 [3C] is added
+// in-kernel; bias_table fp32 [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32 [B*nW, nH, ws*ws]
 ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, void* out,
                                     float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
                                     void* stream) {
@@ -510,19 +794,20 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
   if (ws == 7) {
     const size_t smem = wa::fwd_smem<7>();
     wa::window_attn_fwd_kernel<7><<<dim3(nwin, nH), wa::Cfg<7>::NW * 32, smem, st>>>(
-        (const bf16*)qkv, (const bf16*)qkv_bias, bias_table, (bf16*)out, lse, g, scale);
+        (const bf16*)qkv, (const float*)qkv_bias, bias_table, (bf16*)out, lse, g, scale);
   } else {
     const size_t smem = wa::fwd_smem<14>();
     e = cudaFuncSetAttribute(wa::window_attn_fwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     wa::window_attn_fwd_kernel<14><<<dim3(nwin, nH), wa::Cfg<14>::NW * 32, smem, st>>>(
-        (const bf16*)qkv, (const bf16*)qkv_bias, bias_table, (bf16*)out, lse, g, scale);
+        (const bf16*)qkv, (const float*)qkv_bias, bias_table, (bf16*)out, lse, g, scale);
   }
   ESVIT_LAUNCH_CHECK();
 }
 
-// dqkv bf16 [B,H,W,3C] is fully written; dbias_table fp32 [(2ws-1)^2, nH] and dqkv_bias fp32 [3C] are
-// ACCUMULATED into (caller zero-fills).
+// dqkv bf16 [B,H,W,3C] (grad of the bias-free GEMM output) is fully written; dbias_table fp32 [(2ws-1)^2, nH] and
+// dqkv_bias fp32 [3C] (the COMPLETE qkv-bias gradient: column sums over all window slots, padded ones included)
+// are ACCUMULATED into (caller zero-fills).
 ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, const void* out,
                                     const void* dout, const float* lse, void* dqkv, float* dbias_table,
                                     float* dqkv_bias, int B, int H, int W, int C, int nH, int ws, int shift,
@@ -534,20 +819,21 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
   int gx = (esvit_num_sms() * 8 + nH - 1) / nH;
   if (gx > nwin) gx = nwin;
   if (gx < 1) gx = 1;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  (void)e;
   if (ws == 7) {
-    const size_t smem = wa::bwd_smem<7>();
-    e = cudaFuncSetAttribute(wa::window_attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    wa::window_attn_bwd_kernel<7><<<dim3(gx, nH), wa::Cfg<7>::NW * 32, smem, st>>>(
-        (const bf16*)qkv, (const bf16*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv,
+    const size_t smem = wa::bwd7_smem();
+    gx = (esvit_num_sms() * 16 + nH - 1) / nH;  // 4 CTAs / SM resident, ~4 waves of persistent CTAs
+    if (gx > nwin) gx = nwin;
+    wa::window_attn_bwd7_kernel<<<dim3(gx, nH), 128, smem, st>>>(
+        (const bf16*)qkv, (const float*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv,
         dbias_table, dqkv_bias, g, scale, nwin);
   } else {
     const size_t smem = wa::bwd_smem<14>();
     e = cudaFuncSetAttribute(wa::window_attn_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     wa::window_attn_bwd_kernel<14><<<dim3(gx, nH), wa::Cfg<14>::NW * 32, smem, st>>>(
-        (const bf16*)qkv, (const bf16*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv,
+        (const bf16*)qkv, (const float*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv,
         dbias_table, dqkv_bias, g, scale, nwin);
   }
   ESVIT_LAUNCH_CHECK();

@@ -42,7 +42,7 @@ def _chk(t: Optional[Tensor], dtype, name: str) -> Optional[Tensor]:
 # residual add + LayerNorm
 
 
-def _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, want_y, y_bf16):
+def _add_ln_fwd(x, delta, dbias, keep, tps, gamma, beta, eps, want_y, y_bf16):
     T, C = x.numel() // x.shape[-1], x.shape[-1]
     xout = torch.empty_like(x) if delta is not None else None
     y = mean = rstd = None
@@ -50,24 +50,26 @@ def _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, want_y, y_bf16):
         y = torch.empty(x.shape, dtype=BF16 if y_bf16 else F32, device=x.device)
         mean = torch.empty(T, dtype=F32, device=x.device)
         rstd = torch.empty(T, dtype=F32, device=x.device)
-    _lib.call("esvit_add_ln_fwd", _p(x), _p(delta), _p(keep), tps, _p(gamma), _p(beta), eps, _p(xout), _p(y),
+    _lib.call("esvit_add_ln_fwd", _p(x), _p(delta), _p(dbias), _p(keep), tps, _p(gamma), _p(beta), eps, _p(xout), _p(y),
               1 if y_bf16 else 0, _p(mean), _p(rstd), T, C, _stream())
     return (xout if delta is not None else x), y, mean, rstd
 
 
 class AddLayerNormFn(Function):
-    """(x, delta, keep) -> (xout = x + keep*delta, y = LN(xout)).  keep: per-sample DropPath scale or None."""
+    """(x, delta, delta_bias, keep) -> (xout = x + keep*(delta + delta_bias), y = LN(xout)).
+    keep: per-sample DropPath scale or None; delta_bias: fp32 [C] bias of the bias-free GEMM that made delta, or None."""
 
     @staticmethod
-    def forward(ctx, x, delta, keep, gamma, beta, eps: float, y_bf16: bool):
+    def forward(ctx, x, delta, dbias, keep, gamma, beta, eps: float, y_bf16: bool):
         x = _chk(x, F32, "x")
         delta = _chk(delta, BF16, "delta")
+        dbias = _chk(dbias, F32, "delta_bias")
         keep = _chk(keep, F32, "keep")
         gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
         tps = x.numel() // x.shape[-1] // x.shape[0]
-        xout, y, mean, rstd = _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, True, y_bf16)
+        xout, y, mean, rstd = _add_ln_fwd(x, delta, dbias, keep, tps, gamma, beta, eps, True, y_bf16)
         ctx.save_for_backward(xout, mean, rstd, gamma, keep)
-        ctx.tps, ctx.y_bf16 = tps, y_bf16
+        ctx.tps, ctx.y_bf16, ctx.has_dbias = tps, y_bf16, dbias is not None
         return xout, y
 
     @staticmethod
@@ -80,11 +82,11 @@ class AddLayerNormFn(Function):
             g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
         dx = torch.empty_like(xout)
         ddelta = torch.empty(xout.shape, dtype=BF16, device=xout.device)
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        acc = torch.zeros(3, C, dtype=F32, device=xout.device)  # dgamma | dbeta | ddelta_bias
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, _p(g_xout), _p(xout), _p(mean), _p(rstd),
-                  _p(gamma), _p(keep), ctx.tps, _p(dx), _p(ddelta), _p(dgamma), _p(dbeta), T, C, _stream())
-        return dx, ddelta, None, dgamma, dbeta, None, None
+                  _p(gamma), _p(keep), ctx.tps, _p(dx), _p(ddelta), _p(acc[0]), _p(acc[1]),
+                  _p(acc[2]) if ctx.has_dbias else None, T, C, _stream())
+        return dx, ddelta, (acc[2] if ctx.has_dbias else None), None, acc[0], acc[1], None, None
 
 
 class LayerNormFn(Function):
@@ -94,7 +96,7 @@ class LayerNormFn(Function):
     def forward(ctx, x, gamma, beta, eps: float, y_bf16: bool):
         x = _chk(x, F32, "x")
         gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
-        _, y, mean, rstd = _add_ln_fwd(x, None, None, 1, gamma, beta, eps, True, y_bf16)
+        _, y, mean, rstd = _add_ln_fwd(x, None, None, None, 1, gamma, beta, eps, True, y_bf16)
         ctx.save_for_backward(x, mean, rstd, gamma)
         ctx.y_bf16 = y_bf16
         return y
@@ -106,23 +108,23 @@ class LayerNormFn(Function):
         T, C = x.numel() // x.shape[-1], x.shape[-1]
         g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
         dx = torch.empty_like(x)
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        acc = torch.zeros(2, C, dtype=F32, device=x.device)
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, None, _p(x), _p(mean), _p(rstd), _p(gamma),
-                  None, 1, _p(dx), None, _p(dgamma), _p(dbeta), T, C, _stream())
-        return dx, dgamma, dbeta, None, None
+                  None, 1, _p(dx), None, _p(acc[0]), _p(acc[1]), None, T, C, _stream())
+        return dx, acc[0], acc[1], None, None
 
 
 class ResidualAddFn(Function):
-    """xout = x + keep * delta (fp32 + bf16), no norm."""
+    """xout = x + keep * (delta + delta_bias) (fp32 + bf16), no norm."""
 
     @staticmethod
-    def forward(ctx, x, delta, keep):
+    def forward(ctx, x, delta, dbias, keep):
         x, delta, keep = _chk(x, F32, "x"), _chk(delta, BF16, "delta"), _chk(keep, F32, "keep")
+        dbias = _chk(dbias, F32, "delta_bias")
         tps = x.numel() // x.shape[-1] // x.shape[0]
-        xout, _, _, _ = _add_ln_fwd(x, delta, keep, tps, None, None, 0.0, False, False)
+        xout, _, _, _ = _add_ln_fwd(x, delta, dbias, keep, tps, None, None, 0.0, False, False)
         ctx.save_for_backward(keep)
-        ctx.tps = tps
+        ctx.tps, ctx.has_dbias = tps, dbias is not None
         return xout
 
     @staticmethod
@@ -132,20 +134,22 @@ class ResidualAddFn(Function):
         g = _chk(g, F32, "g")
         T, C = g.numel() // g.shape[-1], g.shape[-1]
         ddelta = torch.empty(g.shape, dtype=BF16, device=g.device)
+        db = torch.zeros(C, dtype=F32, device=g.device) if ctx.has_dbias else None
         _lib.call("esvit_add_ln_bwd", None, 0, _p(g), None, None, None, None, _p(keep), ctx.tps, None, _p(ddelta),
-                  None, None, T, C, _stream())
-        return g, ddelta, None
+                  None, None, _p(db), T, C, _stream())
+        return g, ddelta, db, None
 
 
 def add_layer_norm(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor], gamma: Tensor, beta: Tensor,
-                   eps: float, y_bf16: bool = True) -> Tuple[Tensor, Tensor]:
+                   eps: float, y_bf16: bool = True, delta_bias: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     if delta is None:
         return x, LayerNormFn.apply(x, gamma, beta, eps, y_bf16)
-    return AddLayerNormFn.apply(x, delta, keep, gamma, beta, eps, y_bf16)
+    return AddLayerNormFn.apply(x, delta, delta_bias, keep, gamma, beta, eps, y_bf16)
 
 
-def residual_add(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor]) -> Tensor:
-    return x if delta is None else ResidualAddFn.apply(x, delta, keep)
+def residual_add(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor],
+                 delta_bias: Optional[Tensor] = None) -> Tensor:
+    return x if delta is None else ResidualAddFn.apply(x, delta, delta_bias, keep)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -239,7 +243,8 @@ class PatchEmbedFn(Function):
 
 # ------------------------------------------------------------------------------------------------------------
 class WindowAttentionFn(Function):
-    """qkv bf16 [B, H*W, 3C] -> attention output bf16 [B, H*W, C] in token order (pad/roll/partition folded in)."""
+    """qkv bf16 [B, H*W, 3C] (BIAS-FREE qkv GEMM output) + qkv_bias fp32 [3C] -> attention output bf16 [B, H*W, C]
+    in token order (bias add, pad / roll / partition / reverse folded in); backward returns the full bias gradient."""
 
     @staticmethod
     def forward(ctx, qkv, qkv_bias, bias_table, H: int, W: int, num_heads: int, ws: int, shift: int, scale: float):
@@ -249,7 +254,7 @@ class WindowAttentionFn(Function):
         B, L, C3 = qkv.shape
         C = C3 // 3
         assert L == H * W
-        qb = qkv_bias.to(BF16)
+        qb = qkv_bias
         nwin = B * (-(-H // ws)) * (-(-W // ws))
         out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
         lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
@@ -290,6 +295,30 @@ class GeluFn(Function):
         dx = torch.empty_like(x)
         _lib.call("esvit_gelu_bwd", _p(x), _p(g), _p(dx), x.numel(), _stream())
         return dx
+
+
+class BiasGeluFn(Function):
+    """y = gelu(x + bias) for x bf16 [..., N] from a bias-free GEMM; bias fp32 [N]."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        x, bias = _chk(x, BF16, "x"), _chk(bias, F32, "bias")
+        N = x.shape[-1]
+        y = torch.empty_like(x)
+        _lib.call("esvit_bias_gelu_fwd", _p(x), _p(bias), _p(y), x.numel() // N, N, _stream())
+        ctx.save_for_backward(x, bias)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, bias = ctx.saved_tensors
+        g = _chk(g, BF16, "g")
+        N = x.shape[-1]
+        dx = torch.empty_like(x)
+        db = torch.zeros_like(bias)
+        _lib.call("esvit_bias_gelu_bwd", _p(x), _p(bias), _p(g), _p(dx), _p(db), x.numel() // N, N, _stream())
+        return dx, db
 
 
 class L2NormFn(Function):

@@ -57,10 +57,10 @@ class _CastCache:
 
 
 def _lin_c(x: Tensor, lin: nn.Linear, cc: Optional[_CastCache]) -> Tensor:
-    if cc is None:
-        return _lin(x, lin.weight, lin.bias)
+    """BIAS-FREE bf16 library GEMM x @ W^T.  The bias of `lin` is added by the consumer kernel (window attention,
+    bias+GELU, residual add + LN), which also produces the bias gradient - no separate column-sum kernels."""
     with torch.autocast("cuda", enabled=False):
-        return F.linear(x, cc(lin.weight), cc(lin.bias))
+        return F.linear(x, lin.weight.to(BF16) if cc is None else cc(lin.weight))
 
 
 def drop_path_keep(batch: int, drop_prob: float, training: bool, device) -> Optional[Tensor]:
@@ -83,9 +83,13 @@ class Mlp(nn.Module):
         self.act = nn.GELU()
         self.fc2 = nn.Linear(hidden_features, out_features)
 
-    def forward(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
-        """x bf16 [..., C] -> bf16 [..., C]."""
-        return _lin_c(ops.GeluFn.apply(_lin_c(x, self.fc1, cc)), self.fc2, cc)
+    def fused(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
+        """x bf16 [..., C] -> fc2 GEMM output bf16 WITHOUT fc2.bias (the residual-add kernel adds it)."""
+        return _lin_c(ops.BiasGeluFn.apply(_lin_c(x, self.fc1, cc), self.fc1.bias), self.fc2, cc)
+
+    def forward(self, x: Tensor) -> Tensor:
+        """Reference signature (standalone use): returns fc2(gelu(fc1(x))) including both biases, bf16."""
+        return self.fused(x.to(BF16)) + self.fc2.bias.to(BF16)
 
 
 class WindowAttention(nn.Module):
@@ -113,7 +117,8 @@ class WindowAttention(nn.Module):
         _trunc_normal_(self.relative_position_bias_table, std=.02)
 
     def attend(self, y: Tensor, H: int, W: int, shift: int, cc: Optional[_CastCache] = None) -> Tensor:
-        """y = norm1(x) bf16 [B, H*W, C] in token order -> proj(attention) bf16 [B, H*W, C]."""
+        """y = norm1(x) bf16 [B, H*W, C] in token order -> proj GEMM output bf16 [B, H*W, C] WITHOUT proj.bias
+        (added by the residual-add kernel)."""
         qkv = _lin_c(y, self.qkv, cc)
         a = ops.WindowAttentionFn.apply(qkv, self.qkv.bias, self.relative_position_bias_table, H, W, self.num_heads,
                                         self.window_size[0], shift, float(self.scale))
@@ -128,7 +133,7 @@ class WindowAttention(nn.Module):
         ws = self.window_size[0]
         B_, N, C = x.shape
         assert N == ws * ws
-        return self.attend(x.to(BF16), ws, ws, 0), None
+        return self.attend(x.to(BF16), ws, ws, 0) + self.proj.bias.to(BF16), None
 
 
 class SwinTransformerBlock(nn.Module):
@@ -149,17 +154,19 @@ class SwinTransformerBlock(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def fused(self, x: Tensor, pending, cc: Optional[_CastCache] = None):
-        """(x fp32 [B,L,C], pending=(delta bf16, keep) or None) -> (x, pending) with the MLP add deferred."""
+        """(x fp32 [B,L,C], pending=(delta bf16, keep, delta_bias) or None) -> (x, pending): the MLP branch's
+        residual add (and fc2 bias) is deferred into the next fused add+LN."""
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
-        delta, keep = pending if pending is not None else (None, None)
-        x, y = ops.add_layer_norm(x, delta, keep, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        delta, keep, dbias = pending if pending is not None else (None, None, None)
+        x, y = ops.add_layer_norm(x, delta, keep, self.norm1.weight, self.norm1.bias, self.norm1.eps, delta_bias=dbias)
         a = self.attn.attend(y, H, W, self.shift_size, cc)
         k1 = drop_path_keep(B, self.drop_prob, self.training, x.device)
-        x, y = ops.add_layer_norm(x, a, k1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        z = self.mlp(y, cc)
+        x, y = ops.add_layer_norm(x, a, k1, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                  delta_bias=self.attn.proj.bias)
+        z = self.mlp.fused(y, cc)
         k2 = drop_path_keep(B, self.drop_prob, self.training, x.device)
-        return x, (z, k2)
+        return x, (z, k2, self.mlp.fc2.bias)
 
     def forward(self, x: Tensor):
         """Reference signature: x [B, L, C] -> (x, attn); attn probabilities are not materialised (None)."""
@@ -287,8 +294,9 @@ class SwinTransformer(nn.Module):
         pend = None
         for layer in self.layers:
             x, pend = layer.fused(x, cc)
-        delta, keep = pend if pend is not None else (None, None)
-        _, x_region = ops.add_layer_norm(x, delta, keep, self.norm.weight, self.norm.bias, self.norm.eps, y_bf16=False)
+        delta, keep, dbias = pend if pend is not None else (None, None, None)
+        _, x_region = ops.add_layer_norm(x, delta, keep, self.norm.weight, self.norm.bias, self.norm.eps,
+                                         y_bf16=False, delta_bias=dbias)
         pooled = ops.TokenMeanFn.apply(x_region)
         if self.use_dense_prediction:
             return pooled, x_region

@@ -66,10 +66,13 @@ class DINOHead(nn.Module):
         x = x.to(BF16)
         mods = [self.mlp] if isinstance(self.mlp, nn.Linear) else list(self.mlp)
         with torch.autocast("cuda", enabled=False):
-            for m in mods:
-                if isinstance(m, nn.Linear):
-                    x = F.linear(x, m.weight.to(BF16), m.bias.to(BF16))
+            for i, m in enumerate(mods):
+                if not isinstance(m, nn.Linear):
+                    continue
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU):
+                    # bias-free GEMM; bias add + exact GELU (+ the bias gradient) in one kernel
+                    x = ops.BiasGeluFn.apply(F.linear(x, m.weight.to(BF16)), m.bias)
                 else:
-                    x = ops.GeluFn.apply(x)
+                    x = F.linear(x, m.weight.to(BF16), m.bias.to(BF16))
         x = ops.L2NormFn.apply(x, 1e-12)
         return self.last_layer(x)

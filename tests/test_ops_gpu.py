@@ -110,6 +110,59 @@ def test_patch_embed(E, S):
         assert_close(ps[k].grad, sdr[k].grad, 2e-4, k)
 
 
+@pytest.mark.parametrize("C", [96, 384])
+def test_add_layer_norm_with_fused_branch_bias(C):
+    """xout = x + keep * (delta + bias): the proj / fc2 bias add and its gradient live in the add+LN kernel."""
+    from esvit_b200 import ops
+    torch.manual_seed(C + 1)
+    B, L = 4, 29
+    x = torch.randn(B, L, C)
+    delta = (torch.randn(B, L, C) * 0.5).to(BF16)
+    bias = torch.randn(C) * 0.3
+    keep = torch.tensor([0.0, 1 / 0.8, 1 / 0.8, 0.0])
+    g, b = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    gy, gx = torch.randn(B, L, C).to(BF16).float(), torch.randn(B, L, C)
+    xr, dr, br_, gr, ber = [t.clone().requires_grad_(True) for t in (x, delta.float(), bias, g, b)]
+    xo_r = xr + keep.view(B, 1, 1) * (dr + br_)
+    y_r = F.layer_norm(xo_r, (C,), gr, ber, 1e-6)
+    torch.autograd.backward([xo_r, y_r], [gx, gy])
+    d = _dev()
+    xc, dc, bc_, gc, bec = [t.to(d).requires_grad_(True) for t in (x, delta, bias, g, b)]
+    xo, y = ops.add_layer_norm(xc, dc, keep.to(d), gc, bec, 1e-6, y_bf16=True, delta_bias=bc_)
+    torch.autograd.backward([xo, y], [gx.to(d), gy.to(d).to(BF16)])
+    assert_close(xo, xo_r, 1e-6, "xout")
+    assert_close(y, y_r, 5e-3, "y")
+    assert_close(xc.grad, xr.grad, 1e-4, "dx")
+    assert_close(dc.grad, dr.grad, 5e-3, "ddelta")
+    assert_close(bc_.grad, br_.grad, 1e-4, "dbias")
+    assert_close(gc.grad, gr.grad, 1e-4, "dgamma")
+    # residual add only
+    x3, d3, b3 = x.to(d).requires_grad_(True), delta.to(d).requires_grad_(True), bias.to(d).requires_grad_(True)
+    xo3 = ops.residual_add(x3, d3, keep.to(d), b3)
+    xo3.backward(gx.to(d))
+    assert_close(xo3, xo_r, 1e-6, "add")
+    assert_close(b3.grad, (keep.view(B, 1, 1) * gx).sum((0, 1)), 1e-4, "add dbias")
+
+
+@pytest.mark.parametrize("R,N", [(77, 384), (1000, 2048), (5, 128)])
+def test_bias_gelu(R, N):
+    from esvit_b200 import ops
+    torch.manual_seed(R + N)
+    x = (torch.randn(R, N) * 2).to(BF16)
+    bias = torch.randn(N) * 0.5
+    g = torch.randn(R, N).to(BF16)
+    xr, br_ = x.float().requires_grad_(True), bias.clone().requires_grad_(True)
+    yr = F.gelu(xr + br_)
+    yr.backward(g.float())
+    d = _dev()
+    xc, bc_ = x.to(d).requires_grad_(True), bias.to(d).requires_grad_(True)
+    y = ops.BiasGeluFn.apply(xc, bc_)
+    y.backward(g.to(d))
+    assert_close(y, yr, 4e-3, "bias gelu")
+    assert_close(xc.grad, xr.grad, 5e-3, "dx")
+    assert_close(bc_.grad, br_.grad, 2e-3, "dbias")
+
+
 def test_token_mean():
     from esvit_b200 import ops
     torch.manual_seed(0)
