@@ -497,14 +497,169 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, ws = 7 fast path (KP = 64, one CTA = 4 warps = one (window, head) at a time, persistent over windows).
-// No shared-memory transposition and no atomics in the inner loop:
-//   phase A  warp = 16-query tile : S, P, dP, dS  -> dQ = dS K ;  dS is also summed into register accumulators
-//                                   (this warp's queries x all keys) that become the rel-pos-bias gradient
+// ws = 7 fast path (KP = 64; one CTA = 4 warps = one (window, head) at a time, PERSISTENT over windows).
+//
+// Both kernels were instruction-issue bound in their first version (ncu/profiler: ~40 integer/FP instructions per
+// score element for the rel-pos index arithmetic, bounds checks and expf), not tensor- or HBM-bound.  Here:
+//   * scores live in the log2 domain: s' = acc*(scale*log2e) + bias*log2e (one FMA), P = ex2(s' - m');
+//   * the rel-pos bias of this head is expanded ONCE per persistent CTA - forward: straight into the accumulator
+//     fragment layout in registers; backward: into a [64][72] fp32 shared-memory table - with -inf in the padded
+//     rows/columns, which also replaces every bounds check;
+//   * the shift mask is a template flag, so un-shifted blocks carry no mask code.
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int BLD = 72;  // row stride (floats) of the expanded bias table: 72 % 32 == 8 -> conflict-free float2 reads
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool SHIFT>
+__global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
+    const bf16* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias_table,
+    bf16* __restrict__ out, float* __restrict__ lse, Geo g, float scale, int nwin_total) {
+  constexpr int WS = 7;
+  using C = Cfg<WS>;
+  constexpr int NTHREADS = 128;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + C::KP * LD;
+  bf16* Vs = Ks + C::KP * LD;
+  float* qbs = reinterpret_cast<float*>(Vs + C::KP * LD);
+  int* tok = reinterpret_cast<int*>(qbs + 3 * HD);
+  int* rid = tok + C::KP;
+
+  const int h = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = warp * 16, rA = r0 + (lane >> 2), rB = rA + 8;
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
+  // rel-pos bias of (head h, this warp's 16 query rows) in accumulator-fragment layout, log2 domain
+  float breg[C::NT8][4];
+#pragma unroll
+  for (int nt = 0; nt < C::NT8; nt++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int row = (e < 2) ? rA : rB, col = nt * 8 + (lane & 3) * 2 + (e & 1);
+      float v = 0.f;
+      if (col >= C::NT) v = -INFINITY;
+      else if (row < C::NT) v = bias_table[bias_index<WS>(row, col) * g.nH + h] * LOG2E;
+      breg[nt][e] = v;
+    }
+  const float c = scale * LOG2E;
+  const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
+
+  for (int win = blockIdx.x; win < nwin_total; win += gridDim.x) {
+    const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, b = win / (g.nWx * g.nWy);
+    __syncthreads();
+    if (threadIdx.x < C::KP) {
+      int t = -1, r = 0;
+      if (threadIdx.x < C::NT) slot_info<WS>(g, b, wy, wx, threadIdx.x, t, r);
+      tok[threadIdx.x] = t;
+      rid[threadIdx.x] = r;
+    }
+    __syncthreads();
+    load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
+    __syncthreads();
+
+    uint32_t qa[2][4];
+    ldsm_x4(qa[0], Qs + frag_off);
+    ldsm_x4(qa[1], Qs + frag_off + 16);
+    float acc[C::NT8][4];
+    float m0 = -INFINITY, m1 = -INFINITY;
+    int ridA = 0, ridB = 0;
+    if (SHIFT) { ridA = rid[rA]; ridB = rid[rB]; }
+#pragma unroll
+    for (int nt = 0; nt < C::NT8; nt++) {
+      acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      uint32_t kb[4];
+      ldsm_x4(kb, Ks + (nt * 8 + (lane & 7)) * LD + (lane >> 3) * 8);
+      mma16816(acc[nt], qa[0], kb[0], kb[1]);
+      mma16816(acc[nt], qa[1], kb[2], kb[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[nt][e] = fmaf(acc[nt][e], c, breg[nt][e]);
+      if (SHIFT) {
+        const int2 rc = *reinterpret_cast<const int2*>(rid + nt * 8 + (lane & 3) * 2);
+        if (ridA != rc.x) acc[nt][0] += -100.f * LOG2E;
+        if (ridA != rc.y) acc[nt][1] += -100.f * LOG2E;
+        if (ridB != rc.x) acc[nt][2] += -100.f * LOG2E;
+        if (ridB != rc.y) acc[nt][3] += -100.f * LOG2E;
+      }
+      m0 = fmaxf(m0, fmaxf(acc[nt][0], acc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(acc[nt][2], acc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < C::NT8; nt++) {
+      acc[nt][0] = ex2(acc[nt][0] - m0);
+      acc[nt][1] = ex2(acc[nt][1] - m0);
+      acc[nt][2] = ex2(acc[nt][2] - m1);
+      acc[nt][3] = ex2(acc[nt][3] - m1);
+      s0 += acc[nt][0] + acc[nt][1];
+      s1 += acc[nt][2] + acc[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);
+    if ((lane & 3) == 0) {  // natural-log LSE for the backward
+      float* l = lse + ((long long)win * g.nH + h) * C::NT;
+      if (rA < C::NT) l[rA] = (m0 + lg2(s0)) * LN2;
+      if (rB < C::NT) l[rB] = (m1 + lg2(s1)) * LN2;
+    }
+    float o[4][4];
+#pragma unroll
+    for (int dt = 0; dt < 4; dt++) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < C::MT; kk++) {
+      uint32_t pa[4];
+      pa[0] = pack_bf162(acc[2 * kk][0] * i0, acc[2 * kk][1] * i0);
+      pa[1] = pack_bf162(acc[2 * kk][2] * i1, acc[2 * kk][3] * i1);
+      pa[2] = pack_bf162(acc[2 * kk + 1][0] * i0, acc[2 * kk + 1][1] * i0);
+      pa[3] = pack_bf162(acc[2 * kk + 1][2] * i1, acc[2 * kk + 1][3] * i1);
+      const bf16* vp = Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
+      uint32_t vb[4];
+      ldsm_x4_t(vb, vp);
+      mma16816(o[0], pa, vb[0], vb[1]);
+      mma16816(o[1], pa, vb[2], vb[3]);
+      ldsm_x4_t(vb, vp + 16);
+      mma16816(o[2], pa, vb[0], vb[1]);
+      mma16816(o[3], pa, vb[2], vb[3]);
+    }
+    const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
+#pragma unroll
+    for (int dt = 0; dt < 4; dt++) {
+      const int d = h * HD + dt * 8 + (lane & 3) * 2;
+      if (tA >= 0) *reinterpret_cast<uint32_t*>(out + (long long)tA * g.C + d) = pack_bf162(o[dt][0], o[dt][1]);
+      if (tB >= 0) *reinterpret_cast<uint32_t*>(out + (long long)tB * g.C + d) = pack_bf162(o[dt][2], o[dt][3]);
+    }
+  }
+}
+
+static size_t fwd7_smem() {
+  using C = Cfg<7>;
+  return (size_t)3 * C::KP * LD * 2 + (size_t)3 * HD * 4 + (size_t)2 * C::KP * 4;
+}
+
+// backward: no shared-memory transposition and no atomics in the inner loop.
+//   phase A  warp = 16-query tile : S, P, dP, dS  -> dQ = dS K ;  dS also summed into register accumulators
+//                                   (this warp's queries x all keys, over all windows) = rel-pos-bias gradient
 //   phase B  warp = 16-key tile   : S^T = K Q^T, P^T, dP^T = V dO^T, dS^T recomputed in the transposed layout
 //                                   -> dV = P^T dO, dK = dS^T Q straight from the accumulator fragments
-// Only two __syncthreads per window (smem tile reuse); dqkv-bias gradients are column sums of dQ/dK/dV.
-__global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
+// Two __syncthreads per window (smem tile reuse); dqkv-bias gradients are column sums of dQ / dK / dV.
+template <bool SHIFT>
+__global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
     const bf16* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias_table,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
@@ -518,9 +673,9 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
   bf16* Ks = Qs + C::KP * LD;
   bf16* Vs = Ks + C::KP * LD;
   bf16* dOs = Vs + C::KP * LD;
-  float* bt = reinterpret_cast<float*>(dOs + C::KP * LD);
-  float* dbt = bt + C::NB;
-  float* dqb = dbt + C::NB;
+  float* bm = reinterpret_cast<float*>(dOs + C::KP * LD);  // [64][BLD] expanded bias (log2 domain, -inf padding)
+  float* dbt = bm + C::KP * BLD;                           // [NB] bias-gradient bins
+  float* dqb = dbt + C::NB + 1;                            // (+1 keeps 8-byte alignment of what follows: NB is odd)
   float* qbs = dqb + 3 * HD;
   float* Dsm = qbs + 3 * HD;
   float* Lsm = Dsm + C::KP;
@@ -529,10 +684,12 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
 
   const int h = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < C::NB; i += NTHREADS) {
-    bt[i] = bias_table[i * g.nH + h];
-    dbt[i] = 0.f;
+  for (int i = threadIdx.x; i < C::KP * C::KP; i += NTHREADS) {
+    const int row = i >> 6, col = i & 63;
+    bm[row * BLD + col] = (row < C::NT && col < C::NT) ? bias_table[bias_index<WS>(row, col) * g.nH + h] * LOG2E
+                                                       : -INFINITY;
   }
+  for (int i = threadIdx.x; i < C::NB; i += NTHREADS) dbt[i] = 0.f;
   for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) {
     dqb[i] = 0.f;
     qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
@@ -541,6 +698,7 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
 #pragma unroll
   for (int nt = 0; nt < C::NT8; nt++) dsacc[nt][0] = dsacc[nt][1] = dsacc[nt][2] = dsacc[nt][3] = 0.f;
 
+  const float c = scale * LOG2E;
   const int r0 = warp * 16;                       // this warp's query tile (phase A) / key tile (phase B)
   const int rA = r0 + (lane >> 2), rB = rA + 8;
   const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;  // A-fragment rows of the tile
@@ -554,7 +712,7 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
       if (i < C::NT) slot_info<WS>(g, b, wy, wx, i, t, r);
       tok[i] = t;
       rid[i] = r;
-      Lsm[i] = i < C::NT ? lse[((long long)win * g.nH + h) * C::NT + i] : 0.f;
+      Lsm[i] = i < C::NT ? lse[((long long)win * g.nH + h) * C::NT + i] * LOG2E : 0.f;
     }
     __syncthreads();
     load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
@@ -580,7 +738,8 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
     __syncthreads();
 
     const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
-    const int ridA = rid[rA], ridB = rid[rB];
+    int ridA = 0, ridB = 0;
+    if (SHIFT) { ridA = rid[rA]; ridB = rid[rB]; }
     // ---------------- phase A: rows = queries ----------------
     {
       uint32_t qa[2][4], da[2][4];
@@ -608,20 +767,24 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
           ldsm_x4(kb, Vs + boff);
           mma16816(ds2[hf], da[0], kb[0], kb[1]);
           mma16816(ds2[hf], da[1], kb[2], kb[3]);
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int row = (e < 2) ? rA : rB;
-            const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
-            float dsv = 0.f;
-            if (col < C::NT && row < C::NT) {
-              float sv = sacc[e] * scale + bt[bias_index<WS>(row, col)];
-              if (g.shift > 0 && ((e < 2) ? ridA : ridB) != rid[col]) sv += -100.f;
-              const float pv = __expf(sv - ((e < 2) ? lA : lB));
-              dsv = pv * (ds2[hf][e] - ((e < 2) ? DA : DB));
-            }
-            ds2[hf][e] = dsv;
-            dsacc[nt][e] += dsv;
+          const int c0 = nt * 8 + (lane & 3) * 2;
+          const float2 bA = *reinterpret_cast<const float2*>(bm + rA * BLD + c0);
+          const float2 bB = *reinterpret_cast<const float2*>(bm + rB * BLD + c0);
+          float sv[4] = {fmaf(sacc[0], c, bA.x) - lA, fmaf(sacc[1], c, bA.y) - lA, fmaf(sacc[2], c, bB.x) - lB,
+                         fmaf(sacc[3], c, bB.y) - lB};
+          if (SHIFT) {
+            const int2 rc = *reinterpret_cast<const int2*>(rid + c0);
+            if (ridA != rc.x) sv[0] += -100.f * LOG2E;
+            if (ridA != rc.y) sv[1] += -100.f * LOG2E;
+            if (ridB != rc.x) sv[2] += -100.f * LOG2E;
+            if (ridB != rc.y) sv[3] += -100.f * LOG2E;
           }
+          ds2[hf][0] = ex2(sv[0]) * (ds2[hf][0] - DA);
+          ds2[hf][1] = ex2(sv[1]) * (ds2[hf][1] - DA);
+          ds2[hf][2] = ex2(sv[2]) * (ds2[hf][2] - DB);
+          ds2[hf][3] = ex2(sv[3]) * (ds2[hf][3] - DB);
+#pragma unroll
+          for (int e = 0; e < 4; e++) dsacc[nt][e] += ds2[hf][e];
         }
         uint32_t sa[4];
         sa[0] = pack_bf162(ds2[0][0], ds2[0][1]);
@@ -676,24 +839,24 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
           ldsm_x4(qb, dOs + boff);
           mma16816(dsT[hf], va[0], qb[0], qb[1]);
           mma16816(dsT[hf], va[1], qb[2], qb[3]);
-          const int q0 = nt * 8 + (lane & 3) * 2;
+          const int q0 = nt * 8 + (lane & 3) * 2;  // the two query columns of this thread
           const float2 lq = *reinterpret_cast<const float2*>(Lsm + q0);
           const float2 Dq = *reinterpret_cast<const float2*>(Dsm + q0);
-          const int2 rq = *reinterpret_cast<const int2*>(rid + q0);
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int key = (e < 2) ? rA : rB;
-            const int qry = q0 + (e & 1);
-            float pv = 0.f, dsv = 0.f;
-            if (key < C::NT && qry < C::NT) {
-              float sv = pT[hf][e] * scale + bt[bias_index<WS>(qry, key)];
-              if (g.shift > 0 && ((e < 2) ? ridA : ridB) != ((e & 1) ? rq.y : rq.x)) sv += -100.f;
-              pv = __expf(sv - ((e & 1) ? lq.y : lq.x));
-              dsv = pv * (dsT[hf][e] - ((e & 1) ? Dq.y : Dq.x));
-            }
-            pT[hf][e] = pv;
-            dsT[hf][e] = dsv;
+          // bias[query][key]: rows q0, q0+1 of the table, columns = this thread's key rows
+          float sv[4] = {fmaf(pT[hf][0], c, bm[q0 * BLD + rA]) - lq.x, fmaf(pT[hf][1], c, bm[(q0 + 1) * BLD + rA]) - lq.y,
+                         fmaf(pT[hf][2], c, bm[q0 * BLD + rB]) - lq.x, fmaf(pT[hf][3], c, bm[(q0 + 1) * BLD + rB]) - lq.y};
+          if (SHIFT) {
+            const int2 rq = *reinterpret_cast<const int2*>(rid + q0);
+            if (ridA != rq.x) sv[0] += -100.f * LOG2E;
+            if (ridA != rq.y) sv[1] += -100.f * LOG2E;
+            if (ridB != rq.x) sv[2] += -100.f * LOG2E;
+            if (ridB != rq.y) sv[3] += -100.f * LOG2E;
           }
+          pT[hf][0] = ex2(sv[0]); pT[hf][1] = ex2(sv[1]); pT[hf][2] = ex2(sv[2]); pT[hf][3] = ex2(sv[3]);
+          dsT[hf][0] = pT[hf][0] * (dsT[hf][0] - Dq.x);
+          dsT[hf][1] = pT[hf][1] * (dsT[hf][1] - Dq.y);
+          dsT[hf][2] = pT[hf][2] * (dsT[hf][2] - Dq.x);
+          dsT[hf][3] = pT[hf][3] * (dsT[hf][3] - Dq.y);
         }
         uint32_t pa[4], sa[4];
         pa[0] = pack_bf162(pT[0][0], pT[0][1]);
@@ -737,7 +900,8 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
       colsum_to_smem(dv, 1.f, dqb + 2 * HD, lane);
     }
   }
-  // flush the register-resident rel-pos-bias gradient of this warp's query rows
+  // flush the register-resident rel-pos-bias gradient of this warp's query rows.  dS was formed with
+  // P = ex2(log2-domain score): it is the gradient w.r.t. the natural-domain score, i.e. w.r.t. the table entry.
 #pragma unroll
   for (int nt = 0; nt < C::NT8; nt++)
 #pragma unroll
@@ -754,7 +918,7 @@ __global__ void __launch_bounds__(128, 4) window_attn_bwd7_kernel(
 
 static size_t bwd7_smem() {
   using C = Cfg<7>;
-  return (size_t)4 * C::KP * LD * 2 + (size_t)(2 * C::NB + 6 * HD + 2 * C::KP) * 4 + (size_t)2 * C::KP * 4;
+  return (size_t)4 * C::KP * LD * 2 + (size_t)(C::KP * BLD + C::NB + 1 + 6 * HD + 2 * C::KP) * 4 + (size_t)2 * C::KP * 4;
 }
 
 template <int WS>
@@ -792,9 +956,15 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (ws == 7) {
-    const size_t smem = wa::fwd_smem<7>();
-    wa::window_attn_fwd_kernel<7><<<dim3(nwin, nH), wa::Cfg<7>::NW * 32, smem, st>>>(
-        (const bf16*)qkv, (const float*)qkv_bias, bias_table, (bf16*)out, lse, g, scale);
+    const size_t smem = wa::fwd7_smem();
+    int gx = (esvit_num_sms() * 16 + nH - 1) / nH;  // persistent: ~4 waves of 4 resident CTAs per SM
+    if (gx > nwin) gx = nwin;
+    if (shift > 0)
+      wa::window_attn_fwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(
+          (const bf16*)qkv, (const float*)qkv_bias, bias_table, (bf16*)out, lse, g, scale, nwin);
+    else
+      wa::window_attn_fwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(
+          (const bf16*)qkv, (const float*)qkv_bias, bias_table, (bf16*)out, lse, g, scale, nwin);
   } else {
     const size_t smem = wa::fwd_smem<14>();
     e = cudaFuncSetAttribute(wa::window_attn_fwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -823,11 +993,16 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
   (void)e;
   if (ws == 7) {
     const size_t smem = wa::bwd7_smem();
-    gx = (esvit_num_sms() * 16 + nH - 1) / nH;  // 4 CTAs / SM resident, ~4 waves of persistent CTAs
+    gx = (esvit_num_sms() * 12 + nH - 1) / nH;  // 3 CTAs / SM resident, ~4 waves of persistent CTAs
     if (gx > nwin) gx = nwin;
-    wa::window_attn_bwd7_kernel<<<dim3(gx, nH), 128, smem, st>>>(
-        (const bf16*)qkv, (const float*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv,
-        dbias_table, dqkv_bias, g, scale, nwin);
+    if (shift > 0)
+      wa::window_attn_bwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(
+          (const bf16*)qkv, (const float*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse,
+          (bf16*)dqkv, dbias_table, dqkv_bias, g, scale, nwin);
+    else
+      wa::window_attn_bwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(
+          (const bf16*)qkv, (const float*)qkv_bias, bias_table, (const bf16*)out, (const bf16*)dout, lse,
+          (bf16*)dqkv, dbias_table, dqkv_bias, g, scale, nwin);
   } else {
     const size_t smem = wa::bwd_smem<14>();
     e = cudaFuncSetAttribute(wa::window_attn_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
