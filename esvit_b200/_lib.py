@@ -19,7 +19,7 @@ P, I, L, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 # name -> argtypes (restype is always int).  Keep in sync with include/esvit_b200.h
 # (tests/test_abi.py parses the header and checks names + arity).
 SIGNATURES = {
-    "esvit_add_ln_fwd": [P, P, P, P, I, P, P, F, P, P, I, P, P, L, I, P],
+    "esvit_add_ln_fwd": [P, P, P, I, P, P, F, P, P, I, P, P, L, I, P],
     "esvit_add_ln_bwd": [P, I, P, P, P, P, P, P, I, P, P, P, P, P, L, I, P],
     "esvit_patch_merge_ln_fwd": [P, P, P, F, P, P, P, I, I, I, I, P],
     "esvit_patch_merge_ln_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, P],
@@ -31,8 +31,7 @@ SIGNATURES = {
     "esvit_window_attn_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     "esvit_gelu_fwd": [P, P, L, P],
     "esvit_gelu_bwd": [P, P, P, L, P],
-    "esvit_bias_gelu_fwd": [P, P, P, L, I, P],
-    "esvit_bias_gelu_bwd": [P, P, P, P, P, L, I, P],
+    "esvit_gelu_bwd_dbias": [P, P, P, P, L, I, P],
     "esvit_l2norm_fwd": [P, P, P, F, L, I, P],
     "esvit_l2norm_bwd": [P, P, P, P, L, I, P],
     "esvit_weight_norm_fwd": [P, P, P, P, L, I, P],

@@ -55,39 +55,22 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16x8* __restrict_
   }
 }
 
-// y = gelu(x + bias[col]); x bf16 [R, N], N % 8 == 0
-__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const bf16x8* __restrict__ x, const float* __restrict__ bias,
-                                                            bf16x8* __restrict__ y, long long n8, int N8) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
-       i += (long long)gridDim.x * blockDim.x) {
-    float f[8];
-    unpack8(x[i], f);
-    const int c = (int)(i % N8) * 8;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-    f[0] = gelu_f(f[0] + b0.x); f[1] = gelu_f(f[1] + b0.y); f[2] = gelu_f(f[2] + b0.z); f[3] = gelu_f(f[3] + b0.w);
-    f[4] = gelu_f(f[4] + b1.x); f[5] = gelu_f(f[5] + b1.y); f[6] = gelu_f(f[6] + b1.z); f[7] = gelu_f(f[7] + b1.w);
-    y[i] = pack8(f);
-  }
-}
-
-// dx = dy * gelu'(x + bias); dbias[col] += sum_rows dx.  grid (ceil(N/256), GY), block (32, 8): a thread owns 8
+// dx = dy * gelu'(x) (x already holds the fc1 bias from the GEMM epilogue); dbias[col] += sum_rows dx.  grid (ceil(N/256), GY), block (32, 8): a thread owns 8
 // columns and strides over rows; the 8 row lanes are reduced in shared memory, one atomicAdd per column per CTA.
-__global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ bias,
-                                                            const bf16* __restrict__ dy, bf16* __restrict__ dx,
-                                                            float* __restrict__ dbias, long long R, int N) {
+__global__ void __launch_bounds__(256) gelu_bwd_dbias_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                             bf16* __restrict__ dx, float* __restrict__ dbias,
+                                                             long long R, int N) {
   __shared__ float sh[8][256 + 8];
   const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < N) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + col), b1 = *reinterpret_cast<const float4*>(bias + col + 4);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
       float f[8], g[8];
       unpack8(*reinterpret_cast<const bf16x8*>(x + r * N + col), f);
       unpack8(*reinterpret_cast<const bf16x8*>(dy + r * N + col), g);
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        g[j] *= gelu_grad_f(f[j] + bb[j]);
+        g[j] *= gelu_grad_f(f[j]);
         acc[j] += g[j];
       }
       *reinterpret_cast<bf16x8*>(dx + r * N + col) = pack8(g);
@@ -254,26 +237,18 @@ ESVIT_API int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long 
   ESVIT_LAUNCH_CHECK();
 }
 
-// y = gelu(x + bias) with x bf16 [R, N] (the bias add of the preceding bias-free GEMM is fused here)
-ESVIT_API int esvit_bias_gelu_fwd(const void* x, const float* bias, void* y, long long R, int N, void* stream) {
-  if (N % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
-  const long long n8 = R * N / 8;
-  bias_gelu_fwd_kernel<<<ew_grid(n8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const bf16x8*)x, bias, (bf16x8*)y, n8,
-                                                                               N / 8);
-  ESVIT_LAUNCH_CHECK();
-}
-
-// dx = dy * gelu'(x + bias) (bf16); dbias fp32 [N] ACCUMULATED (caller zero-fills)
-ESVIT_API int esvit_bias_gelu_bwd(const void* x, const float* bias, const void* dy, void* dx, float* dbias,
-                                  long long R, int N, void* stream) {
+// dx = dy * gelu'(x) (bf16) for x bf16 [R, N]; dbias fp32 [N] = column sums of dx (the gradient of the bias the
+// producing GEMM added in its epilogue) ACCUMULATED (caller zero-fills)
+ESVIT_API int esvit_gelu_bwd_dbias(const void* x, const void* dy, void* dx, float* dbias, long long R, int N,
+                                   void* stream) {
   if (N % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
   const int gx = (N + 255) / 256;
   long long gy = ((long long)esvit_num_sms() * 8 + gx - 1) / gx;
   const long long maxgy = (R + 7) / 8;
   if (gy > maxgy) gy = maxgy;
   if (gy < 1) gy = 1;
-  bias_gelu_bwd_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, bias, (const bf16*)dy, (bf16*)dx, dbias, R, N);
+  gelu_bwd_dbias_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)dy, (bf16*)dx, dbias, R, N);
   ESVIT_LAUNCH_CHECK();
 }
 

@@ -35,7 +35,7 @@ __device__ __forceinline__ float sum4(float4 v) { return (v.x + v.y) + (v.z + v.
 // forward: xout = x + keep[b] * delta ; y = LN(xout) * gamma + beta
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
-    const float* __restrict__ x, const bf16* __restrict__ delta, const float* __restrict__ dbias,
+    const float* __restrict__ x, const bf16* __restrict__ delta,
     const float* __restrict__ keep, int tokens_per_sample, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, float* __restrict__ xout, OutT* __restrict__ y,
     float* __restrict__ mean_o, float* __restrict__ rstd_o, long long T, int C) {
@@ -54,10 +54,6 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
         v[i] = Vec4IO<float>::ld(x + row * C + c);
         if (delta) {
           float4 d = Vec4IO<bf16>::ld(delta + row * C + c);
-          if (dbias) {
-            const float4 db = Vec4IO<float>::ld(dbias + c);
-            d.x += db.x; d.y += db.y; d.z += db.z; d.w += db.w;
-          }
           v[i].x += ks * d.x; v[i].y += ks * d.y; v[i].z += ks * d.z; v[i].w += ks * d.w;
           if (xout) Vec4IO<float>::st(xout + row * C + c, v[i]);
         }
@@ -96,7 +92,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
 
 // backward: G = dxo + LNbwd(dy) ; dx = G ; ddelta = keep * G ; dgamma += dy*xhat ; dbeta += dy
 template <int NV, typename DyT>
-__global__ void __launch_bounds__(256) add_ln_bwd_kernel(
+__global__ void __launch_bounds__(128, (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1))) add_ln_bwd_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ dxo, const float* __restrict__ xs,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
     const float* __restrict__ keep, int tokens_per_sample, float* __restrict__ dx, bf16* __restrict__ ddelta,
@@ -366,19 +362,19 @@ int row_grid(long long T, int warps_per_block, int waves) {
   else if ((C_) <= 2048) { CALL(16) }          \
   else return ESVIT_ERR_BAD_ARG;
 
-ESVIT_API int esvit_add_ln_fwd(const float* x, const void* delta, const float* delta_bias, const float* keep,
-                               int tokens_per_sample, const float* gamma, const float* beta, float eps, float* xout,
-                               void* y, int y_is_bf16, float* mean, float* rstd, long long T, int C, void* stream) {
+ESVIT_API int esvit_add_ln_fwd(const float* x, const void* delta, const float* keep, int tokens_per_sample,
+                               const float* gamma, const float* beta, float eps, float* xout, void* y,
+                               int y_is_bf16, float* mean, float* rstd, long long T, int C, void* stream) {
   if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = row_grid(T, 8, 8);
 #define CALL(NV)                                                                                              \
   if (y_is_bf16)                                                                                              \
-    add_ln_fwd_kernel<NV, bf16><<<grid, 256, 0, st>>>(x, (const bf16*)delta, delta_bias, keep,                \
+    add_ln_fwd_kernel<NV, bf16><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep,                            \
                                                       tokens_per_sample, gamma, beta, eps, xout, (bf16*)y,    \
                                                       mean, rstd, T, C);                                      \
   else                                                                                                        \
-    add_ln_fwd_kernel<NV, float><<<grid, 256, 0, st>>>(x, (const bf16*)delta, delta_bias, keep,               \
+    add_ln_fwd_kernel<NV, float><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep,                           \
                                                        tokens_per_sample, gamma, beta, eps, xout, (float*)y,  \
                                                        mean, rstd, T, C);
   DISPATCH_NV(C, CALL)
@@ -392,14 +388,14 @@ ESVIT_API int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo,
                                int C, void* stream) {
   if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = row_grid(T, 8, 4);
+  const int grid = row_grid(T, 4, 16);  // 128-thread CTAs: the per-lane accumulators cost registers, not warps
   const size_t smem = 3 * (size_t)C * sizeof(float);
 #define CALL(NV)                                                                                               \
   if (dy_is_bf16)                                                                                              \
-    add_ln_bwd_kernel<NV, bf16><<<grid, 256, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,    \
+    add_ln_bwd_kernel<NV, bf16><<<grid, 128, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,    \
                                                          tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C); \
   else                                                                                                         \
-    add_ln_bwd_kernel<NV, float><<<grid, 256, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma, keep,  \
+    add_ln_bwd_kernel<NV, float><<<grid, 128, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma, keep,  \
                                                           tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C);
   DISPATCH_NV(C, CALL)
 #undef CALL

@@ -42,7 +42,7 @@ def _chk(t: Optional[Tensor], dtype, name: str) -> Optional[Tensor]:
 # residual add + LayerNorm
 
 
-def _add_ln_fwd(x, delta, dbias, keep, tps, gamma, beta, eps, want_y, y_bf16):
+def _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, want_y, y_bf16):
     T, C = x.numel() // x.shape[-1], x.shape[-1]
     xout = torch.empty_like(x) if delta is not None else None
     y = mean = rstd = None
@@ -50,14 +50,16 @@ def _add_ln_fwd(x, delta, dbias, keep, tps, gamma, beta, eps, want_y, y_bf16):
         y = torch.empty(x.shape, dtype=BF16 if y_bf16 else F32, device=x.device)
         mean = torch.empty(T, dtype=F32, device=x.device)
         rstd = torch.empty(T, dtype=F32, device=x.device)
-    _lib.call("esvit_add_ln_fwd", _p(x), _p(delta), _p(dbias), _p(keep), tps, _p(gamma), _p(beta), eps, _p(xout), _p(y),
+    _lib.call("esvit_add_ln_fwd", _p(x), _p(delta), _p(keep), tps, _p(gamma), _p(beta), eps, _p(xout), _p(y),
               1 if y_bf16 else 0, _p(mean), _p(rstd), T, C, _stream())
     return (xout if delta is not None else x), y, mean, rstd
 
 
 class AddLayerNormFn(Function):
-    """(x, delta, delta_bias, keep) -> (xout = x + keep*(delta + delta_bias), y = LN(xout)).
-    keep: per-sample DropPath scale or None; delta_bias: fp32 [C] bias of the bias-free GEMM that made delta, or None."""
+    """(x, delta, delta_bias, keep) -> (xout = x + keep*delta, y = LN(xout)).
+    keep: per-sample DropPath scale or None.  delta_bias (fp32 [C] parameter or None) is the bias the producing GEMM
+    already added to delta in its epilogue: it is only routed here so that ITS GRADIENT (column sums of ddelta) comes
+    out of this backward kernel instead of a separate reduction."""
 
     @staticmethod
     def forward(ctx, x, delta, dbias, keep, gamma, beta, eps: float, y_bf16: bool):
@@ -67,7 +69,7 @@ class AddLayerNormFn(Function):
         keep = _chk(keep, F32, "keep")
         gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
         tps = x.numel() // x.shape[-1] // x.shape[0]
-        xout, y, mean, rstd = _add_ln_fwd(x, delta, dbias, keep, tps, gamma, beta, eps, True, y_bf16)
+        xout, y, mean, rstd = _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, True, y_bf16)
         ctx.save_for_backward(xout, mean, rstd, gamma, keep)
         ctx.tps, ctx.y_bf16, ctx.has_dbias = tps, y_bf16, dbias is not None
         return xout, y
@@ -96,7 +98,7 @@ class LayerNormFn(Function):
     def forward(ctx, x, gamma, beta, eps: float, y_bf16: bool):
         x = _chk(x, F32, "x")
         gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
-        _, y, mean, rstd = _add_ln_fwd(x, None, None, None, 1, gamma, beta, eps, True, y_bf16)
+        _, y, mean, rstd = _add_ln_fwd(x, None, None, 1, gamma, beta, eps, True, y_bf16)
         ctx.save_for_backward(x, mean, rstd, gamma)
         ctx.y_bf16 = y_bf16
         return y
@@ -115,14 +117,14 @@ class LayerNormFn(Function):
 
 
 class ResidualAddFn(Function):
-    """xout = x + keep * (delta + delta_bias) (fp32 + bf16), no norm."""
+    """xout = x + keep * delta (fp32 + bf16), no norm; delta_bias only receives its gradient (see AddLayerNormFn)."""
 
     @staticmethod
     def forward(ctx, x, delta, dbias, keep):
         x, delta, keep = _chk(x, F32, "x"), _chk(delta, BF16, "delta"), _chk(keep, F32, "keep")
         dbias = _chk(dbias, F32, "delta_bias")
         tps = x.numel() // x.shape[-1] // x.shape[0]
-        xout, _, _, _ = _add_ln_fwd(x, delta, dbias, keep, tps, None, None, 0.0, False, False)
+        xout, _, _, _ = _add_ln_fwd(x, delta, keep, tps, None, None, 0.0, False, False)
         ctx.save_for_backward(keep)
         ctx.tps, ctx.has_dbias = tps, dbias is not None
         return xout
@@ -243,8 +245,9 @@ class PatchEmbedFn(Function):
 
 # ------------------------------------------------------------------------------------------------------------
 class WindowAttentionFn(Function):
-    """qkv bf16 [B, H*W, 3C] (BIAS-FREE qkv GEMM output) + qkv_bias fp32 [3C] -> attention output bf16 [B, H*W, C]
-    in token order (bias add, pad / roll / partition / reverse folded in); backward returns the full bias gradient."""
+    """qkv bf16 [B, H*W, 3C] (qkv GEMM output incl. bias) -> attention output bf16 [B, H*W, C] in token order
+    (pad / roll / partition / reverse folded in).  qkv_bias (fp32 [3C] parameter) supplies the value of padded slots
+    and receives the COMPLETE qkv-bias gradient from the backward kernel (column sums of dq/dk/dv)."""
 
     @staticmethod
     def forward(ctx, qkv, qkv_bias, bias_table, H: int, W: int, num_heads: int, ws: int, shift: int, scale: float):
@@ -254,7 +257,7 @@ class WindowAttentionFn(Function):
         B, L, C3 = qkv.shape
         C = C3 // 3
         assert L == H * W
-        qb = qkv_bias
+        qb = qkv_bias.to(BF16)
         nwin = B * (-(-H // ws)) * (-(-W // ws))
         out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
         lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
@@ -298,27 +301,49 @@ class GeluFn(Function):
 
 
 class BiasGeluFn(Function):
-    """y = gelu(x + bias) for x bf16 [..., N] from a bias-free GEMM; bias fp32 [N]."""
+    """y = gelu(x) for x bf16 [..., N] that already holds the producing GEMM's bias; `bias` (fp32 [N] parameter) only
+    receives its gradient = column sums of dx, computed inside the GELU backward kernel."""
 
     @staticmethod
     def forward(ctx, x, bias):
-        x, bias = _chk(x, BF16, "x"), _chk(bias, F32, "bias")
-        N = x.shape[-1]
+        x = _chk(x, BF16, "x")
         y = torch.empty_like(x)
-        _lib.call("esvit_bias_gelu_fwd", _p(x), _p(bias), _p(y), x.numel() // N, N, _stream())
-        ctx.save_for_backward(x, bias)
+        _lib.call("esvit_gelu_fwd", _p(x), _p(y), x.numel(), _stream())
+        ctx.save_for_backward(x)
+        ctx.bias_meta = (bias.shape, bias.device)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, bias = ctx.saved_tensors
+        (x,) = ctx.saved_tensors
         g = _chk(g, BF16, "g")
         N = x.shape[-1]
         dx = torch.empty_like(x)
-        db = torch.zeros_like(bias)
-        _lib.call("esvit_bias_gelu_bwd", _p(x), _p(bias), _p(g), _p(dx), _p(db), x.numel() // N, N, _stream())
+        db = torch.zeros(ctx.bias_meta[0], dtype=F32, device=ctx.bias_meta[1])
+        _lib.call("esvit_gelu_bwd_dbias", _p(x), _p(g), _p(dx), _p(db), x.numel() // N, N, _stream())
         return dx, db
+
+
+class LinearBiasFn(Function):
+    """y = x @ w^T + b as ONE library GEMM (bias in the cuBLASLt epilogue).  The backward produces dx and dw with two
+    library GEMMs and NO bias gradient: the consumer kernel (window attention / GELU / add+LN backward) column-sums
+    it for free, which removes the reference's per-layer `grad.sum(0)` reduction kernels (10 % of the first profile)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        with torch.autocast("cuda", enabled=False):
+            return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        dx = (g2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = g2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
+        return dx, dw, None
 
 
 class L2NormFn(Function):

@@ -55,12 +55,22 @@ class _CastCache:
             t = self.d[k] = p.to(BF16)
         return t
 
+    def nograd(self, p: Tensor) -> Tensor:
+        k = ("ng", id(p))
+        t = self.d.get(k)
+        if t is None:
+            t = self.d[k] = p.detach().to(BF16)
+        return t
+
 
 def _lin_c(x: Tensor, lin: nn.Linear, cc: Optional[_CastCache]) -> Tensor:
-    """BIAS-FREE bf16 library GEMM x @ W^T.  The bias of `lin` is added by the consumer kernel (window attention,
-    bias+GELU, residual add + LN), which also produces the bias gradient - no separate column-sum kernels."""
-    with torch.autocast("cuda", enabled=False):
-        return F.linear(x, lin.weight.to(BF16) if cc is None else cc(lin.weight))
+    """bf16 library GEMM x @ W^T + b (bias in the GEMM epilogue).  The bias GRADIENT is not computed here: the consumer
+    kernel (window attention / GELU / residual add + LN backward) column-sums it, see ops.LinearBiasFn."""
+    w = lin.weight.to(BF16) if cc is None else cc(lin.weight)
+    if lin.bias is None:
+        with torch.autocast("cuda", enabled=False):
+            return F.linear(x, w)
+    return ops.LinearBiasFn.apply(x, w, (lin.bias.detach().to(BF16) if cc is None else cc.nograd(lin.bias)))
 
 
 def drop_path_keep(batch: int, drop_prob: float, training: bool, device) -> Optional[Tensor]:
@@ -84,12 +94,13 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features, out_features)
 
     def fused(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
-        """x bf16 [..., C] -> fc2 GEMM output bf16 WITHOUT fc2.bias (the residual-add kernel adds it)."""
+        """x bf16 [..., C] -> fc2(gelu(fc1(x))) bf16.  fc1.bias gets its gradient from the GELU backward kernel; the
+        caller must route fc2.bias through the residual-add kernel (ops.add_layer_norm / residual_add delta_bias)."""
         return _lin_c(ops.BiasGeluFn.apply(_lin_c(x, self.fc1, cc), self.fc1.bias), self.fc2, cc)
 
     def forward(self, x: Tensor) -> Tensor:
-        """Reference signature (standalone use): returns fc2(gelu(fc1(x))) including both biases, bf16."""
-        return self.fused(x.to(BF16)) + self.fc2.bias.to(BF16)
+        """Reference signature (standalone use; fc2.bias receives no gradient on this path - use the block)."""
+        return self.fused(x.to(BF16))
 
 
 class WindowAttention(nn.Module):
@@ -117,8 +128,8 @@ class WindowAttention(nn.Module):
         _trunc_normal_(self.relative_position_bias_table, std=.02)
 
     def attend(self, y: Tensor, H: int, W: int, shift: int, cc: Optional[_CastCache] = None) -> Tensor:
-        """y = norm1(x) bf16 [B, H*W, C] in token order -> proj GEMM output bf16 [B, H*W, C] WITHOUT proj.bias
-        (added by the residual-add kernel)."""
+        """y = norm1(x) bf16 [B, H*W, C] in token order -> proj(attention) bf16 [B, H*W, C]; proj.bias gets its gradient
+        from the residual-add kernel the caller routes it through."""
         qkv = _lin_c(y, self.qkv, cc)
         a = ops.WindowAttentionFn.apply(qkv, self.qkv.bias, self.relative_position_bias_table, H, W, self.num_heads,
                                         self.window_size[0], shift, float(self.scale))
@@ -133,7 +144,7 @@ class WindowAttention(nn.Module):
         ws = self.window_size[0]
         B_, N, C = x.shape
         assert N == ws * ws
-        return self.attend(x.to(BF16), ws, ws, 0) + self.proj.bias.to(BF16), None
+        return self.attend(x.to(BF16), ws, ws, 0), None
 
 
 class SwinTransformerBlock(nn.Module):

@@ -70,8 +70,9 @@ class DINOHead(nn.Module):
                 if not isinstance(m, nn.Linear):
                     continue
                 if i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU):
-                    # bias-free GEMM; bias add + exact GELU (+ the bias gradient) in one kernel
-                    x = ops.BiasGeluFn.apply(F.linear(x, m.weight.to(BF16)), m.bias)
+                    # GEMM with bias epilogue; exact GELU kernel whose backward also yields the bias gradient
+                    x = ops.BiasGeluFn.apply(ops.LinearBiasFn.apply(x, m.weight.to(BF16), m.bias.detach().to(BF16)),
+                                             m.bias)
                 else:
                     x = F.linear(x, m.weight.to(BF16), m.bias.to(BF16))
         x = ops.L2NormFn.apply(x, 1e-12)

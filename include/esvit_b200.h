@@ -24,12 +24,12 @@ extern "C" {
 
 /* ---- residual add + LayerNorm ------------------------------------------------------------------------------
  * replaces: x = shortcut + drop_path(branch); y = norm(x)      models/swin_transformer.py:329-331, :283, :687
- * xout = x + keep[row / tokens_per_sample] * (delta + delta_bias) (delta/delta_bias/keep/xout may be NULL; delta_bias
- * is the bias of the bias-free proj / fc2 GEMM that produced delta); y = LN(xout) (y may be NULL).
+ * xout = x + keep[row / tokens_per_sample] * delta (delta/keep/xout may be NULL; delta = proj / fc2 GEMM output
+ * including its bias); y = LN(xout) (y may be NULL).
  * x fp32 [T,C]; delta bf16 [T,C]; keep fp32 [B]; y bf16 or fp32 [T,C]; mean/rstd fp32 [T] (saved for backward). */
-int esvit_add_ln_fwd(const float* x, const void* delta, const float* delta_bias, const float* keep,
-                     int tokens_per_sample, const float* gamma, const float* beta, float eps, float* xout, void* y,
-                     int y_is_bf16, float* mean, float* rstd, long long T, int C, void* stream);
+int esvit_add_ln_fwd(const float* x, const void* delta, const float* keep, int tokens_per_sample,
+                     const float* gamma, const float* beta, float eps, float* xout, void* y, int y_is_bf16,
+                     float* mean, float* rstd, long long T, int C, void* stream);
 /* dx = dxo + LNbwd(dy); ddelta = keep * dx (bf16); dgamma/dbeta/ddelta_bias ACCUMULATED (ddelta_bias = column sums of
  * ddelta = gradient of the proj / fc2 bias).  dy / dxo / dx / ddelta / ddelta_bias may be NULL. */
 int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo, const float* xs, const float* mean,
@@ -59,8 +59,8 @@ int esvit_patch_embed_bwd(const float* img, const float* w, const float* bias, c
 
 /* ---- (shifted-)window attention core ----------------------------- models/swin_transformer.py:120-152, :283-325
  * Folds pad / roll / window_partition / rel-pos bias / -100 shift mask / softmax / PV / window_reverse / roll / crop.
- * qkv bf16 [B,H,W,3C] ([q|k|v][head][32]) is the BIAS-FREE qkv GEMM output; qkv_bias fp32 [3C] is added in-kernel
- * (a padded slot is the bias alone); bias_table fp32 [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32
+ * qkv bf16 [B,H,W,3C] ([q|k|v][head][32]) is the qkv GEMM output including its bias; qkv_bias bf16 [3C] is what a
+ * padded slot holds (the bias alone); bias_table fp32 [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32
  * [B*nWindows, nH, ws*ws].  ws in {7,14}; head_dim 32.
  * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] (complete qkv-bias gradient) ACCUMULATED. */
 int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, void* out, float* lse,
@@ -72,10 +72,9 @@ int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bi
 /* ---- GELU (exact erf), bf16 ------------------------------------------------ models/swin_transformer.py:21-37 */
 int esvit_gelu_fwd(const void* x, void* y, long long n, void* stream);
 int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream);
-/* y = gelu(x + bias[col]) for x bf16 [R,N] (bias of the bias-free fc1 GEMM fused); bwd ACCUMULATES dbias fp32 [N]. */
-int esvit_bias_gelu_fwd(const void* x, const float* bias, void* y, long long R, int N, void* stream);
-int esvit_bias_gelu_bwd(const void* x, const float* bias, const void* dy, void* dx, float* dbias, long long R, int N,
-                        void* stream);
+/* gelu backward that also ACCUMULATES dbias fp32 [N] = column sums of dx for x bf16 [R,N]: the gradient of the fc1
+ * bias (added by the GEMM epilogue) without a separate reduction kernel. */
+int esvit_gelu_bwd_dbias(const void* x, const void* dy, void* dx, float* dbias, long long R, int N, void* stream);
 
 /* ---- DINOHead pieces ------------------------------------------------------ models/vision_transformer.py:403-417
  * l2norm: y = x / max(||x||, eps) rows (bf16); weight_norm: w(bf16) = v * g / ||v||_row (fp32 v [K,D], g [K]). */
