@@ -47,6 +47,8 @@ SIGNATURES = {
     "esvit_region_match": [P, P, I, I, I, I, I, P, P, P],
     "esvit_ema_multi": [P, P, P, I, D, P],
     "esvit_clip_multi": [P, P, I, F, P, P, P],
+    "esvit_grad_sumsq_multi": [P, P, I, P, P],
+    "esvit_adamw_ema_multi": [P, P, P, P, P, P, I, P, P, P, P],
 }
 
 _lib = None
@@ -135,6 +137,10 @@ def call(name: str, *args) -> None:  # noqa: F811  (instrumented wrapper)
         _launch_count += (args[3] + 63) // 64
     elif name == "esvit_clip_multi":
         _launch_count += 2 * ((args[2] + 63) // 64)
+    elif name == "esvit_grad_sumsq_multi":
+        _launch_count += (args[2] + 63) // 64
+    elif name == "esvit_adamw_ema_multi":
+        _launch_count += (args[6] + 31) // 32 + 1
     else:
         _launch_count += _LAUNCHES.get(name, 1)
     if name == _timed_name:

@@ -112,3 +112,116 @@ ESVIT_API int esvit_clip_multi(void* const* grads, const long long* numel, int n
   }
   ESVIT_LAUNCH_CHECK();
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused optimiser pass: per-tensor gradient clip (utils.py:106-115) + AdamW (torch.optim.AdamW semantics,
+// main_esvit.py:411) + teacher EMA (main_esvit.py:587-590) in ONE sweep over the parameters.
+//
+// All step-varying scalars are read from DEVICE memory so that a captured CUDA graph replays with fresh values:
+//   hyper fp32[8]  = {lr, wd_group0, beta1, beta2, eps, ema_m, ema_1m, clip}
+//   state fp32[n*2] per tensor: {step count (as float), flag}  flag bit0 = weight-decayed group, bit1 = skip
+//                    (skip = the reference set p.grad = None: cancel_gradients_last_layer; AdamW then ignores the
+//                    parameter entirely - no decay, no moment update, no step count - while the EMA still runs)
+//   sumsq double[n] = per-tensor sum of squares of the RAW gradient (esvit_grad_sumsq_multi)
+// AdamW per element (torch/optim/adamw.py, amsgrad=False, maximize=False):
+//   p *= 1 - lr*wd ; m = lerp(m, g, 1-b1) ; v = b2*v + (1-b2) g^2 ;
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// EMA: k = fl(fl(k*m) + fl(p_new*(1-m)))  - the two-rounding form of the reference loop, bit-exact.
+namespace {
+
+struct OptList {
+  float* p[MT_MAX / 2];
+  const float* g[MT_MAX / 2];
+  float* m[MT_MAX / 2];
+  float* v[MT_MAX / 2];
+  float* k[MT_MAX / 2];
+  long long n[MT_MAX / 2];
+};
+
+__global__ void __launch_bounds__(256) adamw_ema_kernel(OptList L, const float* __restrict__ hyper,
+                                                        float* __restrict__ state, const double* __restrict__ sumsq,
+                                                        int base) {
+  const int ti = base + blockIdx.y;
+  float* p = L.p[blockIdx.y];
+  const float* g = L.g[blockIdx.y];
+  float* m = L.m[blockIdx.y];
+  float* v = L.v[blockIdx.y];
+  float* k = L.k[blockIdx.y];
+  const long long n = L.n[blockIdx.y];
+  const float lr = hyper[0], wd0 = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4], em = hyper[5],
+              e1m = hyper[6], clip = hyper[7];
+  const int flag = (int)state[2 * ti + 1];
+  const bool skip = (flag & 2) != 0;
+  const float wd = (flag & 1) ? wd0 : 0.f;
+  const float t = state[2 * ti] + 1.f;  // this step's count (bump_steps_kernel advances it after the sweep)
+  float coef = 1.f;
+  if (clip > 0.f) {
+    const float norm = (float)sqrt(sumsq[ti]);
+    const float cc = __fdiv_rn(clip, __fadd_rn(norm, 1e-6f));
+    if (cc < 1.f) coef = cc;
+  }
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n; i += nt) {
+    float pv = p[i];
+    if (!skip) {
+      const float gv = g[i] * coef;
+      float mv = m[i], vv = v[i];
+      pv *= decay;
+      mv = mv + (gv - mv) * (1.f - b1);
+      vv = vv * b2 + (1.f - b2) * gv * gv;
+      const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+      pv -= step_size * (mv / denom);
+      p[i] = pv;
+      m[i] = mv;
+      v[i] = vv;
+    }
+    if (k) k[i] = __fadd_rn(__fmul_rn(k[i], em), __fmul_rn(pv, e1m));
+  }
+}
+
+__global__ void bump_steps_kernel(float* __restrict__ state, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (((int)state[2 * i + 1]) & 2) == 0) state[2 * i] += 1.f;
+}
+
+}  // namespace
+
+// per-tensor sum of squares of fp32 gradients into sumsq double[n] (zeroed here)
+ESVIT_API int esvit_grad_sumsq_multi(void* const* grads, const long long* numel, int n, double* sumsq, void* stream) {
+  if (n < 0) return ESVIT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(double) * (size_t)n, st);
+  if (e != cudaSuccess) return (int)e;
+  for (int base = 0; base < n; base += MT_MAX) {
+    MTList L;
+    const int cnt = n - base < MT_MAX ? n - base : MT_MAX;
+    for (int i = 0; i < cnt; i++) { L.a[i] = grads[base + i]; L.b[i] = nullptr; L.n[i] = numel[base + i]; }
+    sumsq_kernel<<<dim3(64, cnt), 256, 0, st>>>(L, sumsq, base);
+  }
+  ESVIT_LAUNCH_CHECK();
+}
+
+// teacher may be NULL (no EMA); see the comment block above for hyper / state / sumsq
+ESVIT_API int esvit_adamw_ema_multi(void* const* params, const void* const* grads, void* const* exp_avg,
+                                    void* const* exp_avg_sq, void* const* teacher, const long long* numel, int n,
+                                    const float* hyper, float* state, const double* sumsq, void* stream) {
+  if (n < 0) return ESVIT_ERR_BAD_ARG;
+  constexpr int CH = MT_MAX / 2;
+  for (int base = 0; base < n; base += CH) {
+    OptList L;
+    const int cnt = n - base < CH ? n - base : CH;
+    for (int i = 0; i < cnt; i++) {
+      L.p[i] = (float*)params[base + i];
+      L.g[i] = (const float*)grads[base + i];
+      L.m[i] = (float*)exp_avg[base + i];
+      L.v[i] = (float*)exp_avg_sq[base + i];
+      L.k[i] = teacher ? (float*)teacher[base + i] : nullptr;
+      L.n[i] = numel[base + i];
+    }
+    adamw_ema_kernel<<<dim3(64, cnt), 256, 0, (cudaStream_t)stream>>>(L, hyper, state, sumsq, base);
+  }
+  if (n > 0) bump_steps_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, n);
+  ESVIT_LAUNCH_CHECK();
+}

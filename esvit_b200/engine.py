@@ -15,8 +15,11 @@ from typing import List, Optional, Sequence
 import torch
 import torch.nn as nn
 
+import torch.distributed as dist
+
 from . import utils
 from .losses import DDINOLoss, DINOLoss
+from .optim import FusedAdamWEMA
 from .swin_transformer import SwinTransformer
 from .vision_transformer import DINOHead
 
@@ -46,40 +49,102 @@ def build_network(spec: dict, out_dim: int, use_dense_prediction: bool, is_teach
 
 
 class SelfDistillStep:
-    def __init__(self, student: nn.Module, teacher: nn.Module, loss: nn.Module, optimizer: torch.optim.Optimizer,
-                 clip_grad: float = 3.0, freeze_last_layer: int = 1, student_ddp: Optional[nn.Module] = None):
+    """One training step.  optimizer: a torch optimizer (the reference's own sequence: clip kernel, cancel grads,
+    optimizer.step(), EMA kernel) or an esvit_b200.optim.FusedAdamWEMA (clip + AdamW + EMA in one sweep).
+    With use_cuda_graph=True (FusedAdamWEMA only) the whole step - teacher fwd, student fwd/bwd, loss, center update,
+    gradient all-reduce, optimiser sweep - is captured once per (teacher_temp, last-layer-frozen) state and replayed:
+    no Python / launch overhead in the steady state.  lr / wd / momentum live in device memory and are refreshed with
+    an 32-byte async copy before each replay."""
+
+    def __init__(self, student: nn.Module, teacher: nn.Module, loss: nn.Module, optimizer, clip_grad: float = 3.0,
+                 freeze_last_layer: int = 1, student_ddp: Optional[nn.Module] = None, use_cuda_graph: bool = False,
+                 grad_allreduce: bool = False):
         self.student, self.teacher, self.loss, self.opt = student, teacher, loss, optimizer
         self.student_call = student_ddp if student_ddp is not None else student
         self.clip_grad, self.freeze_last_layer = clip_grad, freeze_last_layer
+        self.fused = isinstance(optimizer, FusedAdamWEMA)
+        self.use_cuda_graph = use_cuda_graph and self.fused
+        self.grad_allreduce = grad_allreduce  # own flat all-reduce of the gradients (used instead of DDP in graph mode)
         self.last_norms = None
+        self._graphs = {}
+        self._pool = None
+        self._static_in = None
+        self._static_loss = None
+        self._warm = 0
         for p in self.teacher.parameters():
             p.requires_grad = False
 
-    def __call__(self, images: Sequence[torch.Tensor], epoch: int, lr: float, wd: float, momentum: float) -> torch.Tensor:
-        for i, g in enumerate(self.opt.param_groups):  # main_esvit.py:507-510
-            g["lr"] = lr
-            if i == 0:
-                g["weight_decay"] = wd
-        images = list(images)
+    # ---- the step body (eager; also what gets captured) ---------------------------------------------------
+    def _body(self, images: List[torch.Tensor], epoch: int) -> torch.Tensor:
         with torch.no_grad():
             teacher_output = self.teacher(images[:2])
         student_output = self.student_call(images)
         loss = self.loss(student_output, teacher_output, epoch, None)
-        self.opt.zero_grad(set_to_none=True)
+        if self.fused:
+            self.opt.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=True)
         loss.backward()
-        if self.clip_grad:
-            self.last_norms = utils.clip_gradients(self.student, self.clip_grad)
-        utils.cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)
-        self.opt.step()
-        utils.ema_update(self.student, self.teacher, momentum)
+        if self.grad_allreduce and dist.is_initialized() and dist.get_world_size() > 1:
+            grads = [p.grad for p in self.student.parameters() if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])  # one bandwidth-bound message (295 MB for Swin-T)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        if self.fused:
+            self.opt.step()  # clip + AdamW + EMA, one sweep
+        else:
+            if self.clip_grad:
+                self.last_norms = utils.clip_gradients(self.student, self.clip_grad)
+            utils.cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)
+            self.opt.step()
         return loss.detach()
+
+    def __call__(self, images: Sequence[torch.Tensor], epoch: int, lr: float, wd: float, momentum: float) -> torch.Tensor:
+        images = list(images)
+        if self.fused:
+            self.opt.set_hyper(lr, wd, momentum)
+            self.opt.set_skip_last_layer(epoch < self.freeze_last_layer)
+        else:
+            for i, g in enumerate(self.opt.param_groups):  # main_esvit.py:507-510
+                g["lr"] = lr
+                if i == 0:
+                    g["weight_decay"] = wd
+        if not self.use_cuda_graph:
+            loss = self._body(images, epoch)
+            if not self.fused:
+                utils.ema_update(self.student, self.teacher, momentum)
+            return loss
+        return self._graphed(images, epoch)
+
+    # ---- CUDA-graph path ------------------------------------------------------------------------------------
+    def _graphed(self, images: List[torch.Tensor], epoch: int) -> torch.Tensor:
+        if self._static_in is None:  # adopt the caller's tensors as the graph's static input buffers
+            self._static_in = list(images)
+        for s, im in zip(self._static_in, images):
+            if s.data_ptr() != im.data_ptr():
+                s.copy_(im, non_blocking=True)
+        if self._warm < 3:  # eager warm-up (allocator, cuBLAS workspaces, cached tables) before any capture
+            self._warm += 1
+            return self._body(self._static_in, epoch)
+        key = (float(self.loss.teacher_temp_schedule[epoch]), epoch < self.freeze_last_layer)
+        ent = self._graphs.get(key)
+        if ent is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool):
+                out = self._body(self._static_in, epoch)
+            if self._pool is None:
+                self._pool = g.pool()
+            ent = self._graphs[key] = (g, out)
+        ent[0].replay()
+        return ent[1]
 
 
 def make_step(arch: str = "swin_tiny_w7", out_dim: int = 65536, ncrops: int = 10, dense: bool = True,
               device: str = "cuda", lr: float = 5e-4, weight_decay: float = 0.04, clip_grad: float = 3.0,
               freeze_last_layer: int = 1, drop_path: Optional[float] = None, img_size: int = 224,
               head_kwargs: Optional[dict] = None, spec: Optional[dict] = None, ddp: bool = False,
-              teacher_temp: float = 0.04, seed: int = 0):
+              teacher_temp: float = 0.04, seed: int = 0, optimizer: str = "fused", cuda_graph: bool = False):
     """Build student/teacher/loss/optimizer the way train_esvit does (main_esvit.py:235-435) and return
     (step, student, teacher, loss)."""
     spec = dict(spec if spec is not None else SWIN_SPECS[arch])
@@ -92,8 +157,15 @@ def make_step(arch: str = "swin_tiny_w7", out_dim: int = 65536, ncrops: int = 10
     Loss = DDINOLoss if dense else DINOLoss
     loss = Loss(out_dim, ncrops, teacher_temp, teacher_temp, 0, 100).to(device)
     student_ddp = None
-    if ddp:
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if ddp and multi and optimizer != "fused":
         student_ddp = nn.parallel.DistributedDataParallel(student, device_ids=[torch.cuda.current_device()])
-    opt = torch.optim.AdamW(utils.get_params_groups(student), fused=True)
-    step = SelfDistillStep(student, teacher, loss, opt, clip_grad, freeze_last_layer, student_ddp)
+    if optimizer == "fused":
+        for p in teacher.parameters():
+            p.requires_grad = False
+        opt = FusedAdamWEMA(student, teacher, clip_grad=clip_grad)
+    else:  # the reference's own optimizer object (main_esvit.py:410-415)
+        opt = torch.optim.AdamW(utils.get_params_groups(student), fused=True)
+    step = SelfDistillStep(student, teacher, loss, opt, clip_grad, freeze_last_layer, student_ddp,
+                           use_cuda_graph=cuda_graph, grad_allreduce=(optimizer == "fused" and multi))
     return step, student, teacher, loss

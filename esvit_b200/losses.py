@@ -61,13 +61,20 @@ class _CenteredLoss(nn.Module):
     @torch.no_grad()
     def _reduce_and_update(self, sums: torch.Tensor, rows, names):
         """sums fp32 [n, K] local column sums -> one SUM all-reduce -> EMA of each center (main_esvit.py:650-660).
-        The buffers are REBOUND to new tensors like the reference does: the pending backward reads the old ones."""
+        The buffers are updated IN PLACE (stable addresses: CUDA-graph replays must see the running centers); the
+        loss forward therefore hands autograd a private snapshot of the pre-update center (_snapshot)."""
         world = _world()
         if world > 1:
             dist.all_reduce(sums)
         for i, (name, r) in enumerate(zip(names, rows)):
-            old = getattr(self, name)
-            setattr(self, name, ops.center_ema(old.view(-1), sums[i], r * world, self.center_momentum).view_as(old))
+            c = getattr(self, name).view(-1)
+            ops.center_ema(c, sums[i], r * world, self.center_momentum, out=c)
+
+    @staticmethod
+    def _snapshot(center: torch.Tensor) -> torch.Tensor:
+        """256 KiB copy of a center: what this step's forward AND its (later) backward read, while update_center
+        overwrites the live buffer in between (the reference rebinds self.center to a new tensor instead)."""
+        return center.detach().view(-1).clone()
 
 
 class DINOLoss(_CenteredLoss):
@@ -79,7 +86,7 @@ class DINOLoss(_CenteredLoss):
         temp = float(self.teacher_temp_schedule[epoch])
         n_terms = 2 * self.ncrops - 2
         trow, w = self._cls_tables(B, 1.0 / (n_terms * B), s.device)
-        center = self.center.view(-1)
+        center = self._snapshot(self.center)
         lse_t = ops.row_lse(t, center, 1.0 / temp)
         loss = ops.DinoCEFn.apply(s, t, center, lse_t, trow, w, 1.0 / temp, 1.0 / self.student_temp)
         self.update_center(t)
@@ -118,7 +125,7 @@ class DDINOLoss(_CenteredLoss):
         temp = float(self.teacher_temp_schedule[epoch])
         n_terms = 2 * self.ncrops - 2
         inv_t, inv_s = 1.0 / temp, 1.0 / self.student_temp
-        center, center_grid = self.center.view(-1), self.center_grid.view(-1)
+        center, center_grid = self._snapshot(self.center), self._snapshot(self.center_grid)
 
         # view-level term (0.5 * DINO)
         trow_c, w_c = self._cls_tables(B, 0.5 / (n_terms * B), s_cls.device)

@@ -458,10 +458,12 @@ def colsum(t: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
-def center_ema(center: Tensor, colsum_total: Tensor, rows_total: int, momentum: float) -> Tensor:
-    """Returns a NEW tensor center*m + (colsum/rows)*(1-m) (the loss backward still reads the old center)."""
+def center_ema(center: Tensor, colsum_total: Tensor, rows_total: int, momentum: float,
+               out: Optional[Tensor] = None) -> Tensor:
+    """out = center*m + (colsum/rows)*(1-m); out defaults to a new tensor, out=center updates in place."""
     assert center.is_cuda and center.dtype == F32 and center.is_contiguous()
-    out = torch.empty_like(center)
+    if out is None:
+        out = torch.empty_like(center)
     _lib.call("esvit_center_ema", _p(center), _p(colsum_total), float(rows_total), momentum, _p(out), center.numel(),
               _stream())
     return out

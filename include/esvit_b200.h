@@ -124,6 +124,17 @@ int esvit_ema_multi(void* const* teacher, const void* const* student, const long
                     void* stream);
 int esvit_clip_multi(void* const* grads, const long long* numel, int n, float clip, double* sumsq_ws, float* norms,
                      void* stream);
+/* Fused optimiser pass, CUDA-graph friendly (every step-varying scalar is read from device memory):
+ * grad_sumsq_multi: sumsq[i] = ||grads[i]||^2 (double[n], zeroed inside).
+ * adamw_ema_multi: per-tensor clip (utils.py:106-115) folded into torch.optim.AdamW's update (main_esvit.py:411) and the
+ *   teacher EMA (main_esvit.py:587-590, bit-exact two-rounding form) in one sweep.
+ *   hyper fp32[8] = {lr, wd(group 0), beta1, beta2, eps, ema_m, 1-ema_m, clip(<=0: off)};
+ *   state fp32[2n] = per tensor {step count, flags: bit0 weight-decayed, bit1 skip (= reference's p.grad=None)};
+ *   teacher may be NULL. */
+int esvit_grad_sumsq_multi(void* const* grads, const long long* numel, int n, double* sumsq, void* stream);
+int esvit_adamw_ema_multi(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                          void* const* teacher, const long long* numel, int n, const float* hyper, float* state,
+                          const double* sumsq, void* stream);
 
 #ifdef __cplusplus
 }

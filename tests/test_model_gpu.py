@@ -123,3 +123,23 @@ def test_multicrop_wrapper_equals_model_forward():
     for x, y in zip(a[:3], b[:3]):
         assert torch.equal(x, y)
     assert a[3] == b[3]
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """The captured-and-replayed step computes what the eager step computes (same kernels, same order)."""
+    G = load_golden()
+    stepE, sE, tE, lE, crops, hp = _build(G, True)
+    stepG, sG, tG, lG, _, _ = _build(G, True)
+    stepG.use_cuda_graph = True
+    m = hp["momentum_teacher"]
+    le, lg = [], []
+    for it in range(6):  # 3 eager warm-up calls + capture + 2 replays on the graph side
+        lr = hp["lr"] * (1 + 0.1 * it)
+        le.append(float(stepE(crops, 1, lr, hp["weight_decay"], m)))
+        lg.append(float(stepG(crops, 1, lr, hp["weight_decay"], m)))
+    assert len(stepG._graphs) == 1
+    for a, b in zip(le, lg):
+        assert abs(a - b) < 2e-3 * abs(a), (le, lg)
+    for (n, a), b in zip(sE.named_parameters(), sG.parameters()):
+        assert_close(b, a, 2e-3, n)
+    assert_close(lG.center, lE.center, 1e-3, "center")

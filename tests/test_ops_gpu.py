@@ -438,3 +438,66 @@ def test_clip_gradients_per_tensor():
     assert_close(norms, torch.tensor(norms_r), 1e-5, "norms")
     for a, b in zip(gc, ref):
         assert_close(a, b, 1e-5, "clipped grad")
+
+
+def test_fused_adamw_clip_ema_matches_reference_sequence():
+    """esvit_adamw_ema_multi == utils.clip_gradients -> cancel last_layer grads -> torch.optim.AdamW.step -> EMA loop
+    (main_esvit.py:579-590) on a toy module, over 3 steps with changing lr / wd / momentum."""
+    import torch.nn as nn
+
+    from esvit_b200.optim import FusedAdamWEMA
+    from oracle import losses as L
+
+    class Toy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(33, 65)
+            self.norm = nn.LayerNorm(65)
+            self.last_layer = nn.Linear(65, 130, bias=False)
+            self.g = nn.Parameter(torch.ones(130, 1), requires_grad=False)
+
+    torch.manual_seed(7)
+    ref_s, ref_t = Toy(), Toy()
+    ref_t.load_state_dict(ref_s.state_dict())
+    d = _dev()
+    s, t = Toy().to(d), Toy().to(d)
+    s.load_state_dict(ref_s.state_dict())
+    t.load_state_dict(ref_s.state_dict())
+    for p_ in list(ref_t.parameters()) + list(t.parameters()):
+        p_.requires_grad = False
+    reg = [p_ for n, p_ in ref_s.named_parameters() if p_.requires_grad and not (n.endswith(".bias") or p_.dim() == 1)]
+    noreg = [p_ for n, p_ in ref_s.named_parameters() if p_.requires_grad and (n.endswith(".bias") or p_.dim() == 1)]
+    ropt = torch.optim.AdamW([{"params": reg}, {"params": noreg, "weight_decay": 0.0}])
+    fopt = FusedAdamWEMA(s, t, clip_grad=3.0)
+    g = torch.Generator().manual_seed(8)
+    for it, (lr, wd, mom, skip) in enumerate([(1e-3, 0.04, 0.996, True), (2e-3, 0.05, 0.997, True), (5e-4, 0.1, 0.99, False)]):
+        grads = {n: torch.randn(p_.shape, generator=g) * (20.0 if it % 2 == 0 else 0.05)
+                 for n, p_ in ref_s.named_parameters() if p_.requires_grad}
+        for n, p_ in ref_s.named_parameters():
+            p_.grad = grads[n].clone() if n in grads else None
+        for n, p_ in s.named_parameters():
+            if n in grads:
+                p_.grad.copy_(grads[n])
+        # reference sequence
+        for i, pg in enumerate(ropt.param_groups):
+            pg["lr"] = lr
+            if i == 0:
+                pg["weight_decay"] = wd
+        L.clip_gradients([p_.grad for p_ in ref_s.parameters()], 3.0)
+        if skip:
+            for n, p_ in ref_s.named_parameters():
+                if "last_layer" in n:
+                    p_.grad = None
+        ropt.step()
+        L.ema_update(list(ref_t.parameters()), list(ref_s.parameters()), mom)
+        # fused
+        fopt.set_hyper(lr, wd, mom)
+        fopt.set_skip_last_layer(skip)
+        t_before = [p_.detach().clone() for p_ in t.parameters()]
+        fopt.step()
+        for (n, a), b in zip(s.named_parameters(), ref_s.parameters()):
+            assert_close(a, b, 2e-6, f"param {n} step {it}")
+        for (n, a), b in zip(t.named_parameters(), ref_t.parameters()):
+            assert_close(a, b, 2e-6, f"teacher {n} step {it}")
+        for k0, k1, q in zip(t_before, t.parameters(), s.parameters()):  # EMA bit-exact w.r.t. OUR updated student
+            assert torch.equal(k1, k0.mul_(mom).add_((1 - mom) * q.detach()))
