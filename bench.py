@@ -354,8 +354,12 @@ def main():
                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
                "cpu_baseline": cpu_baseline, "loss": float(l)}
         print(json.dumps(out), flush=True)
+    # Hard exit on every rank: tearing the NCCL communicator down while CUDA graphs that captured collectives are
+    # still alive can block forever (observed at N=2); all results are already reduced and printed.
+    sys.stdout.flush()
+    sys.stderr.flush()
     if dist.is_initialized():
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":
