@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 1 step to this path")
+    ap.add_argument("--min-warmup", type=int, default=3, help="floor on warm-up steps (profiling runs lower it)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as a replayed CUDA graph")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
     return ap.parse_args()
@@ -253,13 +254,14 @@ def main():
     # recorded inside a replayed graph); these steps double as the warm-up the graph capture needs -------------
     _lib.reset_counters()
     _lib.time_entry_point("esvit_dino_ce_bwd")
-    for _ in range(3):
+    n_eager = 3 if args.min_warmup >= 3 else 1
+    for _ in range(n_eager):
         l = one_step(crops)
     torch.cuda.synchronize()
     timed = _lib.timed_results()
-    launches_per_step = _lib.launch_count() // 3
+    launches_per_step = _lib.launch_count() // n_eager
     _lib.time_entry_point(None)
-    for _ in range(max(args.warmup, 3)):  # graph mode: the first of these captures, the rest replay
+    for _ in range(max(args.warmup, args.min_warmup)):  # graph mode: the first of these captures, the rest replay
         l = one_step(crops)
     torch.cuda.synchronize()
     assert torch.isfinite(l).item(), "non-finite loss in warm-up"
@@ -343,7 +345,7 @@ def main():
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
-               "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": WORKLOAD, "arch": args.arch, "batch_per_gpu": B, "global_batch": B * world,
                           "crops": f"2x224^2 + {n_local}x96^2", "out_dim": args.out_dim, "parallelism": f"dp{world}",
