@@ -29,6 +29,7 @@ SIGNATURES = {
     "esvit_patch_embed_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     "esvit_window_attn_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     "esvit_window_attn_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
+    "esvit_gemm_bias_act": [P, P, P, P, P, L, I, I, I, P],
     "esvit_gelu_fwd": [P, P, L, P],
     "esvit_gelu_bwd": [P, P, P, L, P],
     "esvit_gelu_bwd_dbias": [P, P, P, P, L, I, P],
@@ -48,7 +49,7 @@ SIGNATURES = {
     "esvit_ema_multi": [P, P, P, I, D, P],
     "esvit_clip_multi": [P, P, I, F, P, P, P],
     "esvit_grad_sumsq_multi": [P, P, I, P, P],
-    "esvit_adamw_ema_multi": [P, P, P, P, P, P, I, P, P, P, P],
+    "esvit_adamw_ema_multi": [P, P, P, P, P, P, P, P, I, P, P, P, P],
 }
 
 _lib = None
@@ -140,7 +141,7 @@ def call(name: str, *args) -> None:  # noqa: F811  (instrumented wrapper)
     elif name == "esvit_grad_sumsq_multi":
         _launch_count += (args[2] + 63) // 64
     elif name == "esvit_adamw_ema_multi":
-        _launch_count += (args[6] + 31) // 32 + 1
+        _launch_count += (args[8] + 31) // 32 + 1
     else:
         _launch_count += _LAUNCHES.get(name, 1)
     if name == _timed_name:

@@ -12,7 +12,7 @@ namespace {
 // five FMAs instead of erff()'s ~30-instruction path - the GELU kernels are otherwise ALU-bound, not HBM-bound.
 // e = exp(-x^2/2) is shared with the Gaussian pdf of the derivative.
 __device__ __forceinline__ float erf_as(float z_abs, float e) {
-  const float t = __frcp_rn(fmaf(0.3275911f, z_abs, 1.f));
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z_abs, 1.f));  // MUFU.RCP (the IEEE reciprocal costs ~8 instructions)
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

@@ -1,0 +1,304 @@
+// Blackwell-native bf16 GEMM with a fused epilogue:  D[M,N] = act( A[M,K] . W[N,K]^T + bias[N] )   (nn.Linear layout)
+//
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128B-swizzled K-major tiles) into a 4-stage mbarrier ring,
+//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by ONE elected thread, accumulator in TMEM
+//     (128 lanes x 128 columns, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
+//   * epilogue warps read the accumulator with tcgen05.ld, add the bias, optionally apply exact GELU (also storing the
+//     pre-activation that the backward needs) and write bf16 rows straight to HBM.
+// Persistent: grid = #SMs, static round-robin over (m_tile, n_tile) with n fastest so the 128-row A tile is re-read
+// from L2 by neighbouring CTAs.  K/M/N tails rely on TMA zero-fill and an epilogue column/row mask.
+//
+// This is the fc1 (+bias +GELU) GEMM of the Swin MLP (models/swin_transformer.py:31-33) and the generic "Linear" of
+// the block; the descriptor encodings follow the sm_100 UMMA definitions (InstrDescriptor / SmemDescriptor).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace tg {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_EPI_WARPS = 4, NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int TMEM_COLS = 2 * BN;                                          // double-buffered accumulator
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes (64 bf16), 8-row swizzle atoms 1024 B apart.
+// SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+// InstrDescriptor (kind::f16): c_format F32=1 [4,6) | a_format BF16=1 [7,10) | b_format BF16=1 [10,13) |
+// a_major K=0 [15] | b_major K=0 [16] | n_dim=N>>3 [17,23) | m_dim=M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {  // A&S 7.1.26, same polynomial as elementwise.cu
+  const float e = __expf(-0.5f * x * x);
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float er = copysignf(1.f - p * t * e, x);
+  return 0.5f * x * (1.f + er);
+}
+
+struct Params {
+  bf16* out;        // [M, N] act(A W^T + bias)
+  bf16* pre;        // [M, N] pre-activation (A W^T + bias), written when act != 0 and pre != nullptr
+  const float* bias;  // [N] or nullptr
+  int M, N, K, act;   // act: 0 = identity, 1 = exact GELU
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                       const __grid_constant__ CUtensorMap map_b,
+                                                                       const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // [STAGES][A | B], every tile 1024-byte aligned in the SHARED address space (swizzle-128B requirement)
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN, k_blocks = (p.K + BK - 1) / BK;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 2) {  // one warp allocates TMEM (and frees it at the end)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &map_a, &full[stage], kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &map_b, &full[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> registers -> (+bias, GELU) -> bf16 rows in HBM =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), v);
+        if (row < p.M && n0 + c < p.N) {
+          const int ncols = min(32, p.N - (n0 + c));
+          bf16* orow = p.out + (long long)row * p.N + n0 + c;
+          bf16* prow = (p.act && p.pre) ? p.pre + (long long)row * p.N + n0 + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {  // N is a multiple of 8 for every layer of the model (checked on the host)
+              float f[8], g[8];
+#pragma unroll
+              for (int t = 0; t < 8; t++) {
+                f[t] = __uint_as_float(v[j + t]) + (p.bias ? p.bias[n0 + c + j + t] : 0.f);
+                g[t] = p.act ? gelu_erf(f[t]) : f[t];
+              }
+              *reinterpret_cast<bf16x8*>(orow + j) = pack8(g);
+              if (prow) *reinterpret_cast<bf16x8*>(prow + j) = pack8(f);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)ptr;
+  }
+  return fn;
+}
+
+// row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128B swizzle, zero fill out of bounds
+static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
+  EncodeFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tg
+
+// out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]);  act: 0 identity, 1 exact GELU (then `pre`, if not NULL, receives
+// the pre-activation).  a, w bf16 row-major with K contiguous (K % 8 == 0, N % 8 == 0), bias fp32 or NULL.
+ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M,
+                                  int N, int K, int act, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8) || M > 0x7fffffffLL) return ESVIT_ERR_BAD_ARG;
+  CUtensorMap ma, mb;
+  if (!tg::make_map(&ma, a, M, K, tg::BM) || !tg::make_map(&mb, w, N, K, tg::BN)) return ESVIT_ERR_BAD_ARG;
+  tg::Params p;
+  p.out = (bf16*)out; p.pre = (bf16*)pre; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.act = act;
+  const size_t smem = (size_t)tg::STAGES * tg::STAGE_BYTES + (2 * tg::STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tg::gemm_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = (int)((M + tg::BM - 1) / tg::BM) * ((N + tg::BN - 1) / tg::BN);
+  int grid = esvit_num_sms();
+  if (grid > tiles) grid = tiles;
+  tg::gemm_bias_act_kernel<<<grid, tg::NUM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
+  ESVIT_LAUNCH_CHECK();
+}

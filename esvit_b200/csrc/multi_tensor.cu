@@ -135,49 +135,106 @@ struct OptList {
   float* m[MT_MAX / 2];
   float* v[MT_MAX / 2];
   float* k[MT_MAX / 2];
+  bf16* sp[MT_MAX / 2];  // optional bf16 shadow of the updated parameter (GEMM operand of the next step)
+  bf16* sk[MT_MAX / 2];  // optional bf16 shadow of the updated teacher parameter
   long long n[MT_MAX / 2];
 };
+
+struct OptScalars {
+  float decay, b1, b2, eps, step_size, inv_sqrt_bc2, em, e1m, coef;
+  bool skip;
+};
+
+__device__ __forceinline__ void opt_elem(float& pv, float gv, float& mv, float& vv, float& kv, bool has_k,
+                                         const OptScalars& c) {
+  if (!c.skip) {
+    gv *= c.coef;
+    pv *= c.decay;
+    mv = mv + (gv - mv) * (1.f - c.b1);
+    vv = vv * c.b2 + (1.f - c.b2) * gv * gv;
+    const float denom = sqrtf(vv) * c.inv_sqrt_bc2 + c.eps;
+    pv -= c.step_size * (mv / denom);
+  }
+  if (has_k) kv = __fadd_rn(__fmul_rn(kv, c.em), __fmul_rn(pv, c.e1m));
+}
 
 __global__ void __launch_bounds__(256) adamw_ema_kernel(OptList L, const float* __restrict__ hyper,
                                                         float* __restrict__ state, const double* __restrict__ sumsq,
                                                         int base) {
   const int ti = base + blockIdx.y;
+  const long long n = L.n[blockIdx.y];
+  if ((long long)blockIdx.x * blockDim.x * 4 >= n) return;  // big tensors get many CTAs, tiny ones one
   float* p = L.p[blockIdx.y];
   const float* g = L.g[blockIdx.y];
   float* m = L.m[blockIdx.y];
   float* v = L.v[blockIdx.y];
   float* k = L.k[blockIdx.y];
-  const long long n = L.n[blockIdx.y];
-  const float lr = hyper[0], wd0 = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4], em = hyper[5],
-              e1m = hyper[6], clip = hyper[7];
+  bf16* sp = L.sp[blockIdx.y];
+  bf16* sk = L.sk[blockIdx.y];
+  const float lr = hyper[0], wd0 = hyper[1], clip = hyper[7];
   const int flag = (int)state[2 * ti + 1];
-  const bool skip = (flag & 2) != 0;
+  OptScalars c;
+  c.b1 = hyper[2]; c.b2 = hyper[3]; c.eps = hyper[4]; c.em = hyper[5]; c.e1m = hyper[6];
+  c.skip = (flag & 2) != 0;
   const float wd = (flag & 1) ? wd0 : 0.f;
   const float t = state[2 * ti] + 1.f;  // this step's count (bump_steps_kernel advances it after the sweep)
-  float coef = 1.f;
+  c.coef = 1.f;
   if (clip > 0.f) {
     const float norm = (float)sqrt(sumsq[ti]);
     const float cc = __fdiv_rn(clip, __fadd_rn(norm, 1e-6f));
-    if (cc < 1.f) coef = cc;
+    if (cc < 1.f) c.coef = cc;
   }
-  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  const float bc1 = 1.f - powf(c.b1, t), bc2 = 1.f - powf(c.b2, t);
+  c.step_size = lr / bc1;
+  c.inv_sqrt_bc2 = rsqrtf(bc2);
+  c.decay = 1.f - lr * wd;
+  const bool has_k = k != nullptr;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-  for (long long i = tid; i < n; i += nt) {
-    float pv = p[i];
-    if (!skip) {
-      const float gv = g[i] * coef;
-      float mv = m[i], vv = v[i];
-      pv *= decay;
-      mv = mv + (gv - mv) * (1.f - b1);
-      vv = vv * b2 + (1.f - b2) * gv * gv;
-      const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
-      pv -= step_size * (mv / denom);
-      p[i] = pv;
-      m[i] = mv;
-      v[i] = vv;
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)k)) & 15) == 0 &&
+                   ((((uintptr_t)sp) | ((uintptr_t)sk)) & 7) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = tid; i < n4; i += nt) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = make_float4(0, 0, 0, 0), vv = mv, gv = mv, kv = mv;
+    if (!c.skip) {
+      gv = reinterpret_cast<const float4*>(g)[i];
+      mv = reinterpret_cast<float4*>(m)[i];
+      vv = reinterpret_cast<float4*>(v)[i];
     }
-    if (k) k[i] = __fadd_rn(__fmul_rn(k[i], em), __fmul_rn(pv, e1m));
+    if (has_k) kv = reinterpret_cast<float4*>(k)[i];
+    opt_elem(pv.x, gv.x, mv.x, vv.x, kv.x, has_k, c);
+    opt_elem(pv.y, gv.y, mv.y, vv.y, kv.y, has_k, c);
+    opt_elem(pv.z, gv.z, mv.z, vv.z, kv.z, has_k, c);
+    opt_elem(pv.w, gv.w, mv.w, vv.w, kv.w, has_k, c);
+    if (!c.skip) {
+      reinterpret_cast<float4*>(p)[i] = pv;
+      reinterpret_cast<float4*>(m)[i] = mv;
+      reinterpret_cast<float4*>(v)[i] = vv;
+      if (sp) {
+        uint2 u; u.x = pack_bf162(pv.x, pv.y); u.y = pack_bf162(pv.z, pv.w);
+        reinterpret_cast<uint2*>(sp)[i] = u;
+      }
+    }
+    if (has_k) {
+      reinterpret_cast<float4*>(k)[i] = kv;
+      if (sk) {
+        uint2 u; u.x = pack_bf162(kv.x, kv.y); u.y = pack_bf162(kv.z, kv.w);
+        reinterpret_cast<uint2*>(sk)[i] = u;
+      }
+    }
+  }
+  for (long long i = n4 * 4 + tid; i < n; i += nt) {
+    float pv = p[i], mv = 0.f, vv = 0.f, gv = 0.f, kv = 0.f;
+    if (!c.skip) { gv = g[i]; mv = m[i]; vv = v[i]; }
+    if (has_k) kv = k[i];
+    opt_elem(pv, gv, mv, vv, kv, has_k, c);
+    if (!c.skip) {
+      p[i] = pv; m[i] = mv; v[i] = vv;
+      if (sp) sp[i] = __float2bfloat16_rn(pv);
+    }
+    if (has_k) {
+      k[i] = kv;
+      if (sk) sk[i] = __float2bfloat16_rn(kv);
+    }
   }
 }
 
@@ -203,10 +260,12 @@ ESVIT_API int esvit_grad_sumsq_multi(void* const* grads, const long long* numel,
   ESVIT_LAUNCH_CHECK();
 }
 
-// teacher may be NULL (no EMA); see the comment block above for hyper / state / sumsq
+// teacher / param_bf16 / teacher_bf16 may be NULL (no EMA / no bf16 shadows; individual shadow entries may be NULL
+// too); see the comment block above for hyper / state / sumsq
 ESVIT_API int esvit_adamw_ema_multi(void* const* params, const void* const* grads, void* const* exp_avg,
-                                    void* const* exp_avg_sq, void* const* teacher, const long long* numel, int n,
-                                    const float* hyper, float* state, const double* sumsq, void* stream) {
+                                    void* const* exp_avg_sq, void* const* teacher, void* const* param_bf16,
+                                    void* const* teacher_bf16, const long long* numel, int n, const float* hyper,
+                                    float* state, const double* sumsq, void* stream) {
   if (n < 0) return ESVIT_ERR_BAD_ARG;
   constexpr int CH = MT_MAX / 2;
   for (int base = 0; base < n; base += CH) {
@@ -218,9 +277,11 @@ ESVIT_API int esvit_adamw_ema_multi(void* const* params, const void* const* grad
       L.m[i] = (float*)exp_avg[base + i];
       L.v[i] = (float*)exp_avg_sq[base + i];
       L.k[i] = teacher ? (float*)teacher[base + i] : nullptr;
+      L.sp[i] = param_bf16 ? (bf16*)param_bf16[base + i] : nullptr;
+      L.sk[i] = (teacher && teacher_bf16) ? (bf16*)teacher_bf16[base + i] : nullptr;
       L.n[i] = numel[base + i];
     }
-    adamw_ema_kernel<<<dim3(64, cnt), 256, 0, (cudaStream_t)stream>>>(L, hyper, state, sumsq, base);
+    adamw_ema_kernel<<<dim3(512, cnt), 256, 0, (cudaStream_t)stream>>>(L, hyper, state, sumsq, base);
   }
   if (n > 0) bump_steps_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state, n);
   ESVIT_LAUNCH_CHECK();

@@ -27,41 +27,30 @@ __device__ __forceinline__ void issue7(const Geo& g, int win, int h, const bf16*
                                        float* Lraw, int* tok, int* rid) {
   constexpr int WS = 7, NT = 49;
   const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, b = win / (g.nWx * g.nWy);
+  // two threads per window slot: the slot geometry is computed ONCE per thread and reused for its 6 (+4) chunks
+  const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
+  int tk = -1, r = 0;
+  if (t < NT) slot_info<WS>(g, b, wy, wx, t, tk, r);
+  const bf16* src_row = tk >= 0 ? qkv + (long long)tk * 3 * g.C + h * HD : qkv_bias + h * HD;
+  const int nbytes = t < NT ? 16 : 0;  // slots >= 49: zero fill
 #pragma unroll
-  for (int k = 0; k < 6; k++) {  // 64 rows x (q,k,v) x 4 chunks of 16 B = 768 = 6 * 128
-    const int id = threadIdx.x + k * 128;
-    const int t = id / 12, rem = id - t * 12, part = rem >> 2, c16 = rem & 3;
-    bf16* dst = tiles + part * TILE7 + t * LD + c16 * 8;
-    if (t < NT) {
-      int tk, r;
-      slot_info<WS>(g, b, wy, wx, t, tk, r);
-      const bf16* src = tk >= 0 ? qkv + (long long)tk * 3 * g.C + part * g.C + h * HD + c16 * 8
-                                : qkv_bias + part * g.C + h * HD + c16 * 8;
-      cp_async16(dst, src, 16);
-    } else {
-      cp_async16(dst, qkv, 0);
-    }
+  for (int k = 0; k < 6; k++) {  // 12 chunks of 16 B per slot: (q,k,v) x 4; this thread takes 6 consecutive ones
+    const int ch = half * 6 + k, part = ch >> 2, c16 = ch & 3;
+    cp_async16(tiles + part * TILE7 + t * LD + c16 * 8, src_row + part * g.C + c16 * 8, nbytes);
   }
   if (BWD) {
+    const long long off = (long long)(tk >= 0 ? tk : 0) * g.C + h * HD + half * 16;
+    const int nb = tk >= 0 ? 16 : 0;  // padded slots: their output is cropped -> dO = O = 0
 #pragma unroll
-    for (int k = 0; k < 2; k++) {  // 64 rows x 4 chunks = 256 = 2 * 128, for dO and O
-      const int id = threadIdx.x + k * 128;
-      const int t = id >> 2, c16 = id & 3;
-      int tk = -1, r;
-      if (t < NT) slot_info<WS>(g, b, wy, wx, t, tk, r);
-      const long long off = (long long)(tk >= 0 ? tk : 0) * g.C + h * HD + c16 * 8;
-      cp_async16(tiles + 3 * TILE7 + t * LD + c16 * 8, dout + off, tk >= 0 ? 16 : 0);  // padded slots: output cropped
-      cp_async16(tiles + 4 * TILE7 + t * LD + c16 * 8, out + off, tk >= 0 ? 16 : 0);
+    for (int k = 0; k < 2; k++) {
+      cp_async16(tiles + 3 * TILE7 + t * LD + half * 16 + k * 8, dout + off + k * 8, nb);
+      cp_async16(tiles + 4 * TILE7 + t * LD + half * 16 + k * 8, out + off + k * 8, nb);
     }
   }
-  if (threadIdx.x < 64) {
-    int tk = -1, r = 0;
-    if (threadIdx.x < NT) slot_info<WS>(g, b, wy, wx, threadIdx.x, tk, r);
-    tok[threadIdx.x] = tk;
-    rid[threadIdx.x] = r;
-    if (BWD)
-      cp_async4(Lraw + threadIdx.x, lse + ((long long)win * g.nH + h) * NT + (threadIdx.x < NT ? threadIdx.x : 0),
-                threadIdx.x < NT ? 4 : 0);
+  if (half == 0) {
+    tok[t] = tk;
+    rid[t] = r;
+    if (BWD) cp_async4(Lraw + t, lse + ((long long)win * g.nH + h) * NT + (t < NT ? t : 0), t < NT ? 4 : 0);
   }
 }
 
@@ -158,7 +147,7 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
     s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);
+    const float i0 = __fdividef(1.f, s0), i1 = __fdividef(1.f, s1);
     if ((lane & 3) == 0) {  // natural-log LSE for the backward
       float* l = lse + ((long long)win * g.nH + h) * C::NT;
       if (rA < C::NT) l[rA] = (m0 + lg2(s0)) * LN2;

@@ -325,6 +325,19 @@ class BiasGeluFn(Function):
         return dx, db
 
 
+def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, want_pre: bool = False):
+    """tcgen05/TMA GEMM: act(a @ w^T + bias) -> bf16 [M, N] (and the pre-activation when act != 0 and want_pre)."""
+    a, w = _chk(a, BF16, "a"), _chk(w, BF16, "w")
+    bias = _chk(bias, F32, "bias")
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    out = torch.empty(*a.shape[:-1], N, dtype=BF16, device=a.device)
+    pre = torch.empty_like(out) if (act and want_pre) else None
+    _lib.call("esvit_gemm_bias_act", _p(a), _p(w), _p(bias), _p(out), _p(pre), M, N, K, act, _stream())
+    return (out, pre) if (act and want_pre) else out
+
+
 class LinearBiasFn(Function):
     """y = x @ w^T + b as ONE library GEMM (bias in the cuBLASLt epilogue).  The backward produces dx and dw with two
     library GEMMs and NO bias gradient: the consumer kernel (window attention / GELU / add+LN backward) column-sums

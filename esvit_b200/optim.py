@@ -20,7 +20,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
-from . import _lib, ops
+from . import _lib, ops, shadow
 
 F32 = torch.float32
 
@@ -54,20 +54,29 @@ class FusedAdamWEMA:
         self._hyper_host[2], self._hyper_host[3], self._hyper_host[4] = betas[0], betas[1], eps
         self._hyper_host[7] = clip_grad if clip_grad else 0.0
         self.sumsq = torch.zeros(n, dtype=torch.float64, device=dev)
-        # persistent gradient buffers: stable addresses for CUDA-graph capture; zero_grad() clears them in place
-        for p in self.params:
-            if p.requires_grad and p.grad is None:
-                p.grad = torch.zeros_like(p)
+        # bf16 shadows of everything the GEMMs consume (Linear weights and biases); written by the sweep itself
+        def wants_shadow(nm: str, p: torch.Tensor) -> bool:
+            if "relative_position_bias_table" in nm or "patch_embed.proj" in nm or "last_layer" in nm or "norm" in nm:
+                return False
+            return nm.endswith(".weight") and p.dim() == 2 or nm.endswith(".bias")
+
+        self.shadow_p = [shadow.register(p) if wants_shadow(nm, p) else None for nm, p in named]
+        self.shadow_k = None
+        if tparams is not None:
+            self.shadow_k = [shadow.register(k) if wants_shadow(nm, k) else None for (nm, _), k in zip(named, tparams)]
         self._numel = ops._numel_array(self.params)
         self._ptr = {k: ops._ptr_array(v) for k, v in (("p", self.params), ("m", self.exp_avg), ("v", self.exp_avg_sq))}
         self._ptr["k"] = ops._ptr_array(self.teacher_params) if tparams is not None else None
-        self._grad_ptrs()
+        self._ptr["sp"] = self._opt_ptr_array(self.shadow_p)
+        self._ptr["sk"] = self._opt_ptr_array(self.shadow_k) if self.shadow_k is not None else None
         self._skip_last = None
 
-    def _grad_ptrs(self):
-        gs = [(p.grad if p.grad is not None else p) for p in self.params]  # frozen / skipped: dummy pointer, never read
-        self._gkey = tuple(g.data_ptr() for g in gs)
-        self._ptr["g"] = ops._ptr_array(gs)
+    @staticmethod
+    def _opt_ptr_array(tensors):
+        arr = (ctypes.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = t.data_ptr() if t is not None else None
+        return arr
 
     # ---- host-side knobs (tiny async H2D copies; safe between graph replays) ---------------------------------
     def set_hyper(self, lr: float, weight_decay: float, momentum: float) -> None:
@@ -88,19 +97,28 @@ class FusedAdamWEMA:
         self.state[:, 1].copy_(self._flags_host, non_blocking=True)
 
     def zero_grad(self) -> None:
-        grads = [p.grad for p in self.params if p.grad is not None]
-        torch._foreach_zero_(grads)
+        """set_to_none: autograd then writes each gradient straight into a fresh buffer (no += pass).  Under CUDA-graph
+        capture those buffers come from the graph's private pool, so their addresses are stable across replays."""
+        for p in self.params:
+            p.grad = None
 
     @torch.no_grad()
     def step(self) -> None:
-        gkey = tuple((p.grad if p.grad is not None else p).data_ptr() for p in self.params)
-        if gkey != self._gkey:  # someone replaced .grad (e.g. set_to_none): rebuild the pointer table
-            self._grad_ptrs()
+        for p in self.params:
+            g = p.grad
+            if g is not None and not (g.dtype == F32 and g.is_contiguous()):
+                p.grad = g.float().contiguous()
+        gs = [(p.grad if p.grad is not None else p) for p in self.params]  # frozen / cancelled: dummy pointer, never read
+        for i, p in enumerate(self.params):
+            if p.grad is None and not self.frozen[i] and not (self._skip_last and self._last_layer[i] > 0):
+                raise RuntimeError(f"parameter {self.names[i]} received no gradient this step")
+        gptr = ops._ptr_array(gs)
         st = ops._stream()
         n = len(self.params)
-        _lib.call("esvit_grad_sumsq_multi", self._ptr["g"], self._numel, n, ops._p(self.sumsq), st)
-        _lib.call("esvit_adamw_ema_multi", self._ptr["p"], self._ptr["g"], self._ptr["m"], self._ptr["v"], self._ptr["k"],
-                  self._numel, n, ops._p(self.hyper), ops._p(self.state), ops._p(self.sumsq), st)
+        _lib.call("esvit_grad_sumsq_multi", gptr, self._numel, n, ops._p(self.sumsq), st)
+        _lib.call("esvit_adamw_ema_multi", self._ptr["p"], gptr, self._ptr["m"], self._ptr["v"], self._ptr["k"],
+                  self._ptr["sp"], self._ptr["sk"], self._numel, n, ops._p(self.hyper), ops._p(self.state),
+                  ops._p(self.sumsq), st)
 
     def grad_norms(self) -> torch.Tensor:
         """pre-clip per-tensor gradient norms of the last step (device tensor; what clip_gradients returned)."""

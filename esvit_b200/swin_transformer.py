@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, shadow
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -52,25 +52,25 @@ class _CastCache:
         k = id(p)
         t = self.d.get(k)
         if t is None:
-            t = self.d[k] = p.to(BF16)
+            t = self.d[k] = shadow.as_bf16(p)  # optimiser-maintained bf16 shadow when registered, else a cast
         return t
 
     def nograd(self, p: Tensor) -> Tensor:
         k = ("ng", id(p))
         t = self.d.get(k)
         if t is None:
-            t = self.d[k] = p.detach().to(BF16)
+            t = self.d[k] = shadow.as_bf16(p, track_grad=False)
         return t
 
 
 def _lin_c(x: Tensor, lin: nn.Linear, cc: Optional[_CastCache]) -> Tensor:
     """bf16 library GEMM x @ W^T + b (bias in the GEMM epilogue).  The bias GRADIENT is not computed here: the consumer
     kernel (window attention / GELU / residual add + LN backward) column-sums it, see ops.LinearBiasFn."""
-    w = lin.weight.to(BF16) if cc is None else cc(lin.weight)
+    w = shadow.as_bf16(lin.weight) if cc is None else cc(lin.weight)
     if lin.bias is None:
         with torch.autocast("cuda", enabled=False):
             return F.linear(x, w)
-    return ops.LinearBiasFn.apply(x, w, (lin.bias.detach().to(BF16) if cc is None else cc.nograd(lin.bias)))
+    return ops.LinearBiasFn.apply(x, w, (shadow.as_bf16(lin.bias, False) if cc is None else cc.nograd(lin.bias)))
 
 
 def drop_path_keep(batch: int, drop_prob: float, training: bool, device) -> Optional[Tensor]:

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, shadow
 
 BF16 = torch.bfloat16
 
@@ -71,9 +71,9 @@ class DINOHead(nn.Module):
                     continue
                 if i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU):
                     # GEMM with bias epilogue; exact GELU kernel whose backward also yields the bias gradient
-                    x = ops.BiasGeluFn.apply(ops.LinearBiasFn.apply(x, m.weight.to(BF16), m.bias.detach().to(BF16)),
-                                             m.bias)
+                    x = ops.BiasGeluFn.apply(
+                        ops.LinearBiasFn.apply(x, shadow.as_bf16(m.weight), shadow.as_bf16(m.bias, False)), m.bias)
                 else:
-                    x = F.linear(x, m.weight.to(BF16), m.bias.to(BF16))
+                    x = F.linear(x, shadow.as_bf16(m.weight), shadow.as_bf16(m.bias))
         x = ops.L2NormFn.apply(x, 1e-12)
         return self.last_layer(x)

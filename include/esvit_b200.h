@@ -69,6 +69,13 @@ int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bi
                           const void* dout, const float* lse, void* dqkv, float* dbias_table, float* dqkv_bias, int B,
                           int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
 
+/* ---- tcgen05 / TMA GEMM with fused epilogue ------------------------- nn.Linear + Mlp.act, models/swin_transformer.py:31-33
+ * out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]); act 0 = identity, 1 = exact GELU (then `pre`, if not NULL, gets the
+ * pre-activation the backward needs).  a, w bf16 row-major (K contiguous), K % 8 == 0, N % 8 == 0, bias fp32 or NULL.
+ * TMA-staged 128B-swizzled tiles, tcgen05.mma with the fp32 accumulator in TMEM, persistent over output tiles. */
+int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M, int N, int K,
+                        int act, void* stream);
+
 /* ---- GELU (exact erf), bf16 ------------------------------------------------ models/swin_transformer.py:21-37 */
 int esvit_gelu_fwd(const void* x, void* y, long long n, void* stream);
 int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream);
@@ -130,11 +137,13 @@ int esvit_clip_multi(void* const* grads, const long long* numel, int n, float cl
  *   teacher EMA (main_esvit.py:587-590, bit-exact two-rounding form) in one sweep.
  *   hyper fp32[8] = {lr, wd(group 0), beta1, beta2, eps, ema_m, 1-ema_m, clip(<=0: off)};
  *   state fp32[2n] = per tensor {step count, flags: bit0 weight-decayed, bit1 skip (= reference's p.grad=None)};
- *   teacher may be NULL. */
+ *   teacher may be NULL; param_bf16 / teacher_bf16 (arrays or entries may be NULL) receive bf16 copies of the updated
+ *   values = the GEMM operands of the next step, so no per-step cast kernels are needed. */
 int esvit_grad_sumsq_multi(void* const* grads, const long long* numel, int n, double* sumsq, void* stream);
 int esvit_adamw_ema_multi(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
-                          void* const* teacher, const long long* numel, int n, const float* hyper, float* state,
-                          const double* sumsq, void* stream);
+                          void* const* teacher, void* const* param_bf16, void* const* teacher_bf16,
+                          const long long* numel, int n, const float* hyper, float* state, const double* sumsq,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,8 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 if [ "$1" != "nobench_tests" ]; then
+timeout 240 python -m pytest tests/test_gemm_tcgen05_gpu.py -m gpu -q --timeout 120 -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/test_gemm.log
+echo "== tcgen05 gemm: $(tail -1 gpurun_out/test_gemm.log)"; grep -E "tcgen05 gemm\+" gpurun_out/test_gemm.log
 for f in test_ops_gpu test_model_gpu; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -150 > gpurun_out/$f.log
   echo "== $f: $(tail -1 gpurun_out/$f.log)"
