@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
 
 // backward: G = dxo + LNbwd(dy) ; dx = G ; ddelta = keep * G ; dgamma += dy*xhat ; dbeta += dy
 template <int NV, typename DyT>
-__global__ void __launch_bounds__(128, (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1))) add_ln_bwd_kernel(
+__global__ void __launch_bounds__(NV <= 2 ? 256 : 128, (NV <= 2 ? 2 : (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1)))) add_ln_bwd_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ dxo, const float* __restrict__ xs,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
     const float* __restrict__ keep, int tokens_per_sample, float* __restrict__ dx, bf16* __restrict__ ddelta,
@@ -388,14 +388,17 @@ ESVIT_API int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo,
                                int C, void* stream) {
   if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = row_grid(T, 4, 16);  // 128-thread CTAs: the per-lane accumulators cost registers, not warps
+  // wide rows: 128-thread CTAs (the per-lane accumulators cost registers, not warps); narrow rows: fewer, larger CTAs
+  // (every CTA ends with 3*C global atomics - thousands of CTAs on a 96-wide row would serialise on them)
+  const int threads = C <= 256 ? 256 : 128;
+  const int grid = C <= 256 ? row_grid(T, 8, 4) : row_grid(T, 4, 16);
   const size_t smem = 3 * (size_t)C * sizeof(float);
 #define CALL(NV)                                                                                               \
   if (dy_is_bf16)                                                                                              \
-    add_ln_bwd_kernel<NV, bf16><<<grid, 128, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,    \
+    add_ln_bwd_kernel<NV, bf16><<<grid, threads, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,    \
                                                          tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C); \
   else                                                                                                         \
-    add_ln_bwd_kernel<NV, float><<<grid, 128, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma, keep,  \
+    add_ln_bwd_kernel<NV, float><<<grid, threads, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma, keep,  \
                                                           tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C);
   DISPATCH_NV(C, CALL)
 #undef CALL

@@ -27,30 +27,30 @@ __device__ __forceinline__ void issue7(const Geo& g, int win, int h, const bf16*
                                        float* Lraw, int* tok, int* rid) {
   constexpr int WS = 7, NT = 49;
   const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, b = win / (g.nWx * g.nWy);
-  // two threads per window slot: the slot geometry is computed ONCE per thread and reused for its 6 (+4) chunks
-  const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
-  int tk = -1, r = 0;
-  if (t < NT) slot_info<WS>(g, b, wy, wx, t, tk, r);
-  const bf16* src_row = tk >= 0 ? qkv + (long long)tk * 3 * g.C + h * HD : qkv_bias + h * HD;
-  const int nbytes = t < NT ? 16 : 0;  // slots >= 49: zero fill
+  // 4 adjacent lanes cover one 64-byte (slot, q|k|v) segment (coalesced like a row copy); a thread serves the SAME
+  // two slots for all of q, k, v (+ dO, O), so the slot geometry is computed twice per thread per window, not 6-10x.
+  const int c16 = threadIdx.x & 3;
 #pragma unroll
-  for (int k = 0; k < 6; k++) {  // 12 chunks of 16 B per slot: (q,k,v) x 4; this thread takes 6 consecutive ones
-    const int ch = half * 6 + k, part = ch >> 2, c16 = ch & 3;
-    cp_async16(tiles + part * TILE7 + t * LD + c16 * 8, src_row + part * g.C + c16 * 8, nbytes);
-  }
-  if (BWD) {
-    const long long off = (long long)(tk >= 0 ? tk : 0) * g.C + h * HD + half * 16;
-    const int nb = tk >= 0 ? 16 : 0;  // padded slots: their output is cropped -> dO = O = 0
+  for (int kk = 0; kk < 2; kk++) {
+    const int t = (threadIdx.x >> 2) + 32 * kk;
+    int tk = -1, r = 0;
+    if (t < NT) slot_info<WS>(g, b, wy, wx, t, tk, r);
+    const bf16* src_row = (tk >= 0 ? qkv + (long long)tk * 3 * g.C : qkv_bias) + h * HD + c16 * 8;
+    const int nbytes = t < NT ? 16 : 0;  // slots >= 49: zero fill
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      cp_async16(tiles + 3 * TILE7 + t * LD + half * 16 + k * 8, dout + off + k * 8, nb);
-      cp_async16(tiles + 4 * TILE7 + t * LD + half * 16 + k * 8, out + off + k * 8, nb);
+    for (int part = 0; part < 3; part++)
+      cp_async16(tiles + part * TILE7 + t * LD + c16 * 8, src_row + part * g.C, nbytes);
+    if (BWD) {
+      const long long off = (long long)(tk >= 0 ? tk : 0) * g.C + h * HD + c16 * 8;
+      const int nb = tk >= 0 ? 16 : 0;  // padded slots: their output is cropped -> dO = O = 0
+      cp_async16(tiles + 3 * TILE7 + t * LD + c16 * 8, dout + off, nb);
+      cp_async16(tiles + 4 * TILE7 + t * LD + c16 * 8, out + off, nb);
     }
-  }
-  if (half == 0) {
-    tok[t] = tk;
-    rid[t] = r;
-    if (BWD) cp_async4(Lraw + t, lse + ((long long)win * g.nH + h) * NT + (t < NT ? t : 0), t < NT ? 4 : 0);
+    if (c16 == 0) {
+      tok[t] = tk;
+      rid[t] = r;
+      if (BWD) cp_async4(Lraw + t, lse + ((long long)win * g.nH + h) * NT + (t < NT ? t : 0), t < NT ? 4 : 0);
+    }
   }
 }
 

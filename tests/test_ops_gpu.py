@@ -476,8 +476,7 @@ def test_fused_adamw_clip_ema_matches_reference_sequence():
         for n, p_ in ref_s.named_parameters():
             p_.grad = grads[n].clone() if n in grads else None
         for n, p_ in s.named_parameters():
-            if n in grads:
-                p_.grad.copy_(grads[n])
+            p_.grad = grads[n].clone().to(d) if n in grads else None
         # reference sequence
         for i, pg in enumerate(ropt.param_groups):
             pg["lr"] = lr
