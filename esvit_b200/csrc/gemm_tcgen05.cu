@@ -3,8 +3,9 @@
 //   * operands staged by TMA (cp.async.bulk.tensor.2d, 128B-swizzled K-major tiles) into a 4-stage mbarrier ring,
 //   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by ONE elected thread, accumulator in TMEM
 //     (128 lanes x 128 columns, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
-//   * epilogue warps read the accumulator with tcgen05.ld, add the bias, optionally apply exact GELU (also storing the
-//     pre-activation that the backward needs) and write bf16 rows straight to HBM.
+//   * 8 epilogue warps read the accumulator with tcgen05.ld, add the bias, optionally apply exact GELU (also keeping the
+//     pre-activation that the backward needs), stage bf16 tiles in 128B-swizzled shared memory and hand them to TMA
+//     stores (cp.async.bulk.tensor ... global.shared::cta), which also clip the M / N tails.
 // Persistent: grid = #SMs, static round-robin over (m_tile, n_tile) with n fastest so the 128-row A tile is re-read
 // from L2 by neighbouring CTAs.  K/M/N tails rely on TMA zero-fill and an epilogue column/row mask.
 //
@@ -19,8 +20,10 @@ namespace tg {
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_EPI_WARPS = 4, NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int NUM_EPI_WARPS = 8, NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-9 epilogue
 constexpr int TMEM_COLS = 2 * BN;                                          // double-buffered accumulator
+constexpr int OUT_TILE_BYTES = BM * BN * 2;                                // bf16 staging tile of the TMA store
+constexpr int OUT_HALF_BYTES = BM * 64 * 2;                                // one 64-column (128-byte) swizzled box
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -56,6 +59,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -127,11 +136,15 @@ struct Params {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                        const __grid_constant__ CUtensorMap map_b,
+                                                                       const __grid_constant__ CUtensorMap map_out,
+                                                                       const __grid_constant__ CUtensorMap map_pre,
                                                                        const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // [STAGES][A | B], every tile 1024-byte aligned in the SHARED address space (swizzle-128B requirement)
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint8_t* stage_out = tiles + STAGES * STAGE_BYTES;  // [2 halves][128 rows][128 B] swizzled, for `out`
+  uint8_t* stage_pre = stage_out + OUT_TILE_BYTES;    // same for the pre-activation
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_pre + OUT_TILE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
@@ -206,8 +219,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
       }
     }
   } else {
-    // ===================== epilogue warps: TMEM -> registers -> (+bias, GELU) -> bf16 rows in HBM =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps: TMEM -> registers -> (+bias, GELU) -> swizzled smem -> TMA store ==========
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int colhalf = (warp - 2) >> 2;       // warps 2-5: columns 0..63, warps 6-9: columns 64..127
+    const bool store_pre = p.act && p.pre;
+    const int r = q * 32 + lane;               // row of the tile owned by this thread
+    uint8_t* so = stage_out + colhalf * OUT_HALF_BYTES + r * 128;
+    uint8_t* sp = stage_pre + colhalf * OUT_HALF_BYTES + r * 128;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
       const int as = local & 1;
@@ -215,33 +233,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       mbar_wait(&tmem_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), v);
-        if (row < p.M && n0 + c < p.N) {
-          const int ncols = min(32, p.N - (n0 + c));
-          bf16* orow = p.out + (long long)row * p.N + n0 + c;
-          bf16* prow = (p.act && p.pre) ? p.pre + (long long)row * p.N + n0 + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {  // N is a multiple of 8 for every layer of the model (checked on the host)
-              float f[8], g[8];
-#pragma unroll
-              for (int t = 0; t < 8; t++) {
-                f[t] = __uint_as_float(v[j + t]) + (p.bias ? p.bias[n0 + c + j + t] : 0.f);
-                g[t] = p.act ? gelu_erf(f[t]) : f[t];
-              }
-              *reinterpret_cast<bf16x8*>(orow + j) = pack8(g);
-              if (prow) *reinterpret_cast<bf16x8*>(prow + j) = pack8(f);
-            }
-          }
-        }
-      }
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + colhalf * 64);
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      mbar_arrive(&tmem_empty[as]);
+      mbar_arrive(&tmem_empty[as]);  // accumulator drained into registers: the MMA warp may start the next-but-one tile
+      // the previous tile's TMA stores must have finished READING the staging tiles before they are overwritten
+      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      epi_bar();
+#pragma unroll
+      for (int j = 0; j < 8; j++) {  // 8 chunks of 8 columns = 16 B
+        const int cbase = n0 + colhalf * 64 + j * 8;
+        float f[8], g[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          const uint32_t raw = (j < 4) ? v0[(j & 3) * 8 + t] : v1[(j & 3) * 8 + t];
+          f[t] = __uint_as_float(raw) + ((p.bias && cbase + t < p.N) ? p.bias[cbase + t] : 0.f);
+          g[t] = p.act ? gelu_erf(f[t]) : f[t];
+        }
+        const int sw = (j ^ (r & 7)) * 16;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+        *reinterpret_cast<bf16x8*>(so + sw) = pack8(g);
+        if (store_pre) *reinterpret_cast<bf16x8*>(sp + sw) = pack8(f);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy smem writes -> visible to TMA
+      epi_bar();
+      if (threadIdx.x == 64) {
+        tma_store_2d(&map_out, stage_out, n0, m0);
+        if (n0 + 64 < p.N) tma_store_2d(&map_out, stage_out + OUT_HALF_BYTES, n0 + 64, m0);
+        if (store_pre) {
+          tma_store_2d(&map_pre, stage_pre, n0, m0);
+          if (n0 + 64 < p.N) tma_store_2d(&map_pre, stage_pre + OUT_HALF_BYTES, n0 + 64, m0);
+        }
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
     }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // stores complete before exit
   }
   __syncthreads();
   if (warp == 2) {
@@ -285,11 +312,14 @@ static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M,
                                   int N, int K, int act, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8) || M > 0x7fffffffLL) return ESVIT_ERR_BAD_ARG;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, mp;
   if (!tg::make_map(&ma, a, M, K, tg::BM) || !tg::make_map(&mb, w, N, K, tg::BN)) return ESVIT_ERR_BAD_ARG;
+  if (!tg::make_map(&mo, out, M, N, tg::BM) || !tg::make_map(&mp, (act && pre) ? pre : out, M, N, tg::BM))
+    return ESVIT_ERR_BAD_ARG;
   tg::Params p;
   p.out = (bf16*)out; p.pre = (bf16*)pre; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.act = act;
-  const size_t smem = (size_t)tg::STAGES * tg::STAGE_BYTES + (2 * tg::STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = (size_t)tg::STAGES * tg::STAGE_BYTES + 2 * tg::OUT_TILE_BYTES +
+                      (2 * tg::STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tg::gemm_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -299,6 +329,6 @@ ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bia
   const int tiles = (int)((M + tg::BM - 1) / tg::BM) * ((N + tg::BN - 1) / tg::BN);
   int grid = esvit_num_sms();
   if (grid > tiles) grid = tiles;
-  tg::gemm_bias_act_kernel<<<grid, tg::NUM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
+  tg::gemm_bias_act_kernel<<<grid, tg::NUM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, mp, p);
   ESVIT_LAUNCH_CHECK();
 }

@@ -183,6 +183,209 @@ __global__ void __launch_bounds__(128, 1) patch_embed_bwd_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// v2: register-tiled kernels.  The first version spent its time on shared-memory weight reads and shuffles (1 LDS per
+// FMA); here a 256-thread CTA owns a 64-token x E tile with the gathered patches A[48][64] and the weights W[48][E]
+// in shared memory, and every thread accumulates a 4-token x (E/16)-channel micro-tile: (1 + E/16) LDS per
+// 4*E/16 FMAs.  LN statistics are 16-lane shuffles (a token's channels live in one half-warp).
+constexpr int PE_TM = 64;        // tokens per tile
+constexpr int PE_LDA = PE_TM + 4;  // padded row stride of A / dconv tiles (floats): 68 % 32 = 4 -> conflict-free float4
+
+template <int EJ>
+__device__ __forceinline__ void pe_gather_tile(const float* __restrict__ img, float* As, long long t0, long long T,
+                                               int Ht, int Wt, int H, int W) {
+  // 64 tokens x 12 (channel, dy) rows of 4 contiguous pixels = 768 float4 loads; lanes = consecutive tokens (coalesced)
+#pragma unroll
+  for (int it = 0; it < 3; it++) {
+    const int f = threadIdx.x + it * 256;
+    const int tok = f & 63, cdy = f >> 6;
+    const long long gt = t0 + tok;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gt < T) {
+      const int tx = (int)(gt % Wt), ty = (int)((gt / Wt) % Ht), b = (int)(gt / ((long long)Wt * Ht));
+      const int c = cdy >> 2, dy = cdy & 3;
+      v = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + c) * H + ty * 4 + dy) * W + tx * 4);
+    }
+    As[(cdy * 4 + 0) * PE_LDA + tok] = v.x;
+    As[(cdy * 4 + 1) * PE_LDA + tok] = v.y;
+    As[(cdy * 4 + 2) * PE_LDA + tok] = v.z;
+    As[(cdy * 4 + 3) * PE_LDA + tok] = v.w;
+  }
+}
+
+template <int EJ>
+__device__ __forceinline__ void pe_conv_tile(const float* As, const float* Ws, const float* bj, int E, int tg, int cg,
+                                             float (&acc)[4][EJ]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < EJ; j++) acc[i][j] = bj[j];
+#pragma unroll 4
+  for (int k = 0; k < PE_K; k++) {
+    const float4 a = *reinterpret_cast<const float4*>(As + k * PE_LDA + tg * 4);
+    float wv[EJ];
+#pragma unroll
+    for (int j = 0; j < EJ; j++) wv[j] = Ws[k * E + cg + 16 * j];
+#pragma unroll
+    for (int j = 0; j < EJ; j++) {
+      acc[0][j] = fmaf(a.x, wv[j], acc[0][j]);
+      acc[1][j] = fmaf(a.y, wv[j], acc[1][j]);
+      acc[2][j] = fmaf(a.z, wv[j], acc[2][j]);
+      acc[3][j] = fmaf(a.w, wv[j], acc[3][j]);
+    }
+  }
+}
+
+__device__ __forceinline__ float half_warp_sum(float v) {  // over the 16 lanes that share a token group
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int EJ>
+__global__ void __launch_bounds__(256) patch_embed_fwd2_kernel(
+    const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ out,
+    float* __restrict__ mean_o, float* __restrict__ rstd_o, int B, int H, int W) {
+  constexpr int E = 16 * EJ;
+  extern __shared__ float smem[];
+  float* Ws = smem;             // [48][E]
+  float* As = Ws + PE_K * E;    // [48][PE_LDA]
+  for (int i = threadIdx.x; i < PE_K * E; i += 256) {
+    const int e = i / PE_K, k = i - e * PE_K;
+    Ws[k * E + e] = w[i];
+  }
+  const int cg = threadIdx.x & 15, tg = threadIdx.x >> 4;
+  const int Ht = H / 4, Wt = W / 4;
+  const long long T = (long long)B * Ht * Wt;
+  float bj[EJ], gj[EJ], bej[EJ];
+#pragma unroll
+  for (int j = 0; j < EJ; j++) { bj[j] = bias[cg + 16 * j]; gj[j] = gamma[cg + 16 * j]; bej[j] = beta[cg + 16 * j]; }
+  const float invE = 1.f / (float)E;
+  for (long long t0 = (long long)blockIdx.x * PE_TM; t0 < T; t0 += (long long)gridDim.x * PE_TM) {
+    __syncthreads();
+    pe_gather_tile<EJ>(img, As, t0, T, Ht, Wt, H, W);
+    __syncthreads();
+    float acc[4][EJ];
+    pe_conv_tile<EJ>(As, Ws, bj, E, tg, cg, acc);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < EJ; j++) s += acc[i][j];
+      const float mean = half_warp_sum(s) * invE;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < EJ; j++) { const float d = acc[i][j] - mean; q += d * d; }
+      const float rstd = rsqrtf(half_warp_sum(q) * invE + eps);
+      const long long gt = t0 + tg * 4 + i;
+      if (gt < T) {
+#pragma unroll
+        for (int j = 0; j < EJ; j++) out[gt * E + cg + 16 * j] = (acc[i][j] - mean) * rstd * gj[j] + bej[j];
+        if (cg == 0) { mean_o[gt] = mean; rstd_o[gt] = rstd; }
+      }
+    }
+  }
+}
+
+template <int EJ>
+__global__ void __launch_bounds__(256) patch_embed_bwd2_kernel(
+    const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+    const float* __restrict__ gamma, const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
+    const float* __restrict__ dout, float* __restrict__ dw, float* __restrict__ dbias, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, int B, int H, int W) {
+  constexpr int E = 16 * EJ;
+  extern __shared__ float smem[];
+  float* Ws = smem;                    // [48][E]
+  float* As = Ws + PE_K * E;           // [48][PE_LDA]   gathered patches, k-major
+  float* Ds = As + PE_K * PE_LDA;      // [E][PE_LDA]    dconv, channel-major
+  float* red = Ds + E * PE_LDA;        // [3][E]         dbias | dgamma | dbeta partial sums
+  for (int i = threadIdx.x; i < PE_K * E; i += 256) {
+    const int e = i / PE_K, k = i - e * PE_K;
+    Ws[k * E + e] = w[i];
+  }
+  for (int i = threadIdx.x; i < 3 * E; i += 256) red[i] = 0.f;
+  const int cg = threadIdx.x & 15, tg = threadIdx.x >> 4;
+  const int Ht = H / 4, Wt = W / 4;
+  const long long T = (long long)B * Ht * Wt;
+  float bj[EJ], gj[EJ];
+#pragma unroll
+  for (int j = 0; j < EJ; j++) { bj[j] = bias[cg + 16 * j]; gj[j] = gamma[cg + 16 * j]; }
+  const float invE = 1.f / (float)E;
+  float adw[3][EJ], adb[EJ], adg[EJ], adbe[EJ];  // this thread's dW[e = cg+16j][k = tg*3 + kk] and per-channel sums
+#pragma unroll
+  for (int j = 0; j < EJ; j++) {
+    adb[j] = adg[j] = adbe[j] = 0.f;
+    adw[0][j] = adw[1][j] = adw[2][j] = 0.f;
+  }
+  for (long long t0 = (long long)blockIdx.x * PE_TM; t0 < T; t0 += (long long)gridDim.x * PE_TM) {
+    __syncthreads();
+    pe_gather_tile<EJ>(img, As, t0, T, Ht, Wt, H, W);
+    __syncthreads();
+    float acc[4][EJ];
+    pe_conv_tile<EJ>(As, Ws, bj, E, tg, cg, acc);
+    float dc[4][EJ];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const long long gt = t0 + tg * 4 + i;
+      const bool ok = gt < T;
+      const float mean = ok ? mean_i[gt] : 0.f, rstd = ok ? rstd_i[gt] : 0.f;
+      float gy[EJ], xh[EJ], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < EJ; j++) {
+        const float d = ok ? dout[gt * E + cg + 16 * j] : 0.f;
+        xh[j] = (acc[i][j] - mean) * rstd;
+        gy[j] = d * gj[j];
+        s1 += gy[j];
+        s2 += gy[j] * xh[j];
+        adg[j] += d * xh[j];
+        adbe[j] += d;
+      }
+      s1 = half_warp_sum(s1) * invE;
+      s2 = half_warp_sum(s2) * invE;
+#pragma unroll
+      for (int j = 0; j < EJ; j++) {
+        dc[i][j] = rstd * (gy[j] - s1 - xh[j] * s2);
+        adb[j] += dc[i][j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EJ; j++)
+      *reinterpret_cast<float4*>(Ds + (cg + 16 * j) * PE_LDA + tg * 4) = make_float4(dc[0][j], dc[1][j], dc[2][j], dc[3][j]);
+    __syncthreads();
+    // dW[e][k] += sum_tokens dconv[token][e] * A[token][k]   (thread: k = tg*3..+2, e = cg + 16 j)
+#pragma unroll 4
+    for (int t4 = 0; t4 < PE_TM / 4; t4++) {
+      float4 a[3];
+#pragma unroll
+      for (int kk = 0; kk < 3; kk++) a[kk] = *reinterpret_cast<const float4*>(As + (tg * 3 + kk) * PE_LDA + t4 * 4);
+#pragma unroll
+      for (int j = 0; j < EJ; j++) {
+        const float4 d = *reinterpret_cast<const float4*>(Ds + (cg + 16 * j) * PE_LDA + t4 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++)
+          adw[kk][j] += (a[kk].x * d.x + a[kk].y * d.y) + (a[kk].z * d.z + a[kk].w * d.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < EJ; j++) {
+    const int e = cg + 16 * j;
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) atomicAdd(&dw[e * PE_K + tg * 3 + kk], adw[kk][j]);
+    atomicAdd(&red[e], adb[j]);
+    atomicAdd(&red[E + e], adg[j]);
+    atomicAdd(&red[2 * E + e], adbe[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += 256) {
+    atomicAdd(&dbias[i], red[i]);
+    atomicAdd(&dgamma[i], red[E + i]);
+    atomicAdd(&dbeta[i], red[2 * E + i]);
+  }
+}
+
 }  // namespace
 
 #define PE_DISPATCH(E_, CALL)        \
@@ -197,6 +400,22 @@ ESVIT_API int esvit_patch_embed_fwd(const float* img, const float* w, const floa
                                     const float* beta, float eps, float* out, float* mean, float* rstd, int B, int H,
                                     int W, int E, void* stream) {
   if (H % 4 || W % 4 || B <= 0) return ESVIT_ERR_BAD_ARG;
+  if (E % 16 == 0 && E <= 128 && E >= 32) {  // register-tiled v2
+    const long long T = (long long)B * (H / 4) * (W / 4);
+    long long need = (T + PE_TM - 1) / PE_TM, cap = (long long)esvit_num_sms() * 4;
+    const int grid2 = (int)(need < cap ? need : cap);
+    const size_t smem2 = (size_t)(PE_K * E + PE_K * PE_LDA) * sizeof(float);
+#define CALL2(EJ) patch_embed_fwd2_kernel<EJ><<<grid2, 256, smem2, (cudaStream_t)stream>>>(img, w, bias, gamma, beta, eps, out, mean, rstd, B, H, W);
+    switch (E / 16) {
+      case 2: CALL2(2) break;
+      case 4: CALL2(4) break;
+      case 6: CALL2(6) break;
+      case 8: CALL2(8) break;
+      default: return ESVIT_ERR_BAD_ARG;
+    }
+#undef CALL2
+    ESVIT_LAUNCH_CHECK();
+  }
   const long long ngroups = (long long)B * (H / 4) * ((W / 4 + 7) / 8);
   long long need = (ngroups + 3) / 4, cap = (long long)esvit_num_sms() * 8;
   const int grid = (int)(need < cap ? need : cap);
@@ -213,6 +432,29 @@ ESVIT_API int esvit_patch_embed_bwd(const float* img, const float* w, const floa
                                     const float* mean, const float* rstd, const float* dout, float* dw, float* dbias,
                                     float* dgamma, float* dbeta, int B, int H, int W, int E, void* stream) {
   if (H % 4 || W % 4 || B <= 0) return ESVIT_ERR_BAD_ARG;
+  if (E % 16 == 0 && E <= 128 && E >= 32) {  // register-tiled v2
+    const long long T = (long long)B * (H / 4) * (W / 4);
+    long long need = (T + PE_TM - 1) / PE_TM, cap = (long long)esvit_num_sms() * 2;
+    const int grid2 = (int)(need < cap ? need : cap);
+    const size_t smem2 = (size_t)(PE_K * E + PE_K * PE_LDA + E * PE_LDA + 3 * E) * sizeof(float);
+#define CALL2(EJ)                                                                                                  \
+  {                                                                                                                \
+    cudaError_t e2 = cudaFuncSetAttribute(patch_embed_bwd2_kernel<EJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem2);                                                             \
+    if (e2 != cudaSuccess) return (int)e2;                                                                         \
+    patch_embed_bwd2_kernel<EJ><<<grid2, 256, smem2, (cudaStream_t)stream>>>(img, w, bias, gamma, mean, rstd, dout, \
+                                                                             dw, dbias, dgamma, dbeta, B, H, W);   \
+  }
+    switch (E / 16) {
+      case 2: CALL2(2) break;
+      case 4: CALL2(4) break;
+      case 6: CALL2(6) break;
+      case 8: CALL2(8) break;
+      default: return ESVIT_ERR_BAD_ARG;
+    }
+#undef CALL2
+    ESVIT_LAUNCH_CHECK();
+  }
   const long long ngroups = (long long)B * (H / 4) * ((W / 4 + 7) / 8);
   long long need = (ngroups + 3) / 4, cap = (long long)esvit_num_sms() * 2;
   const int grid = (int)(need < cap ? need : cap);

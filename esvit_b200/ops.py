@@ -338,6 +338,33 @@ def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, wa
     return (out, pre) if (act and want_pre) else out
 
 
+class LinearGeluFn(Function):
+    """gelu(x @ w^T + b) as ONE tcgen05/TMA kernel (esvit_gemm_bias_act): the GEMM epilogue adds the bias, applies the
+    exact GELU and also stores the pre-activation, so the [T, 4C] hidden tensor is written once and never re-read in
+    the forward.  Backward: GELU' + bias gradient in one kernel, then dx / dw as library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        out, pre = gemm_bias_act(x, w, bias, act=1, want_pre=True)
+        ctx.save_for_backward(x, w, pre)
+        ctx.bias_meta = (bias.shape, bias.device)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w, pre = ctx.saved_tensors
+        g = _chk(g, BF16, "g")
+        N = pre.shape[-1]
+        dh = torch.empty_like(pre)
+        db = torch.zeros(ctx.bias_meta[0], dtype=F32, device=ctx.bias_meta[1])
+        _lib.call("esvit_gelu_bwd_dbias", _p(pre), _p(g), _p(dh), _p(db), pre.numel() // N, N, _stream())
+        dh2 = dh.reshape(-1, N)
+        dx = (dh2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = dh2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
+        return dx, dw, db
+
+
 class LinearBiasFn(Function):
     """y = x @ w^T + b as ONE library GEMM (bias in the cuBLASLt epilogue).  The backward produces dx and dw with two
     library GEMMs and NO bias gradient: the consumer kernel (window attention / GELU / add+LN backward) column-sums

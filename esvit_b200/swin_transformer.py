@@ -17,6 +17,7 @@ Execution model (what differs from the reference):
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 from typing import Dict, List, Optional, Tuple
 
@@ -28,6 +29,10 @@ from . import ops, shadow
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
+
+
+# fc1 + bias + exact GELU as one tcgen05/TMA GEMM (esvit_gemm_bias_act) instead of library GEMM + GELU kernel
+USE_TCGEN05_FC1 = os.environ.get("ESVIT_TCGEN05_FC1", "1") != "0"
 
 
 def _trunc_normal_(t: Tensor, std: float = .02) -> Tensor:
@@ -96,7 +101,12 @@ class Mlp(nn.Module):
     def fused(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
         """x bf16 [..., C] -> fc2(gelu(fc1(x))) bf16.  fc1.bias gets its gradient from the GELU backward kernel; the
         caller must route fc2.bias through the residual-add kernel (ops.add_layer_norm / residual_add delta_bias)."""
-        return _lin_c(ops.BiasGeluFn.apply(_lin_c(x, self.fc1, cc), self.fc1.bias), self.fc2, cc)
+        if USE_TCGEN05_FC1:
+            w1 = shadow.as_bf16(self.fc1.weight) if cc is None else cc(self.fc1.weight)
+            h = ops.LinearGeluFn.apply(x, w1, self.fc1.bias)
+        else:
+            h = ops.BiasGeluFn.apply(_lin_c(x, self.fc1, cc), self.fc1.bias)
+        return _lin_c(h, self.fc2, cc)
 
     def forward(self, x: Tensor) -> Tensor:
         """Reference signature (standalone use; fc2.bias receives no gradient on this path - use the block)."""
