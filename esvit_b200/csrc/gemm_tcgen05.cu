@@ -3,7 +3,7 @@
 //   * operands staged by TMA (cp.async.bulk.tensor.2d, 128B-swizzled K-major tiles) into a 4-stage mbarrier ring,
 //   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by ONE elected thread, accumulator in TMEM
 //     (128 lanes x 128 columns, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
-//   * 8 epilogue warps read the accumulator with tcgen05.ld, add the bias, optionally apply exact GELU (also keeping the
+//   * 16 epilogue warps (the bias + exact-GELU math is latency-bound, it needs the warps) read the accumulator with tcgen05.ld, add the bias, optionally apply exact GELU (also keeping the
 //     pre-activation that the backward needs), stage bf16 tiles in 128B-swizzled shared memory and hand them to TMA
 //     stores (cp.async.bulk.tensor ... global.shared::cta), which also clip the M / N tails.
 // Persistent: grid = #SMs, static round-robin over (m_tile, n_tile) with n fastest so the 128-row A tile is re-read
@@ -17,10 +17,10 @@
 
 namespace tg {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_EPI_WARPS = 8, NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-9 epilogue
+constexpr int NUM_EPI_WARPS = 16, NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-17 epilogue
 constexpr int TMEM_COLS = 2 * BN;                                          // double-buffered accumulator
 constexpr int OUT_TILE_BYTES = BM * BN * 2;                                // bf16 staging tile of the TMA store
 constexpr int OUT_HALF_BYTES = BM * 64 * 2;                                // one 64-column (128-byte) swizzled box
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // [STAGES][A | B], every tile 1024-byte aligned in the SHARED address space (swizzle-128B requirement)
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stage_out = tiles + STAGES * STAGE_BYTES;  // [2 halves][128 rows][128 B] swizzled, for `out`
-  uint8_t* stage_pre = stage_out + OUT_TILE_BYTES;    // same for the pre-activation
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage_pre + OUT_TILE_BYTES);
+  // store staging, double-buffered over tiles: [2 buffers][out | pre][2 halves][128 rows][128 B] (128B-swizzled)
+  uint8_t* stage_base = tiles + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + 4 * OUT_TILE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
@@ -221,38 +221,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
   } else {
     // ===================== epilogue warps: TMEM -> registers -> (+bias, GELU) -> swizzled smem -> TMA store ==========
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int colhalf = (warp - 2) >> 2;       // warps 2-5: columns 0..63, warps 6-9: columns 64..127
+    const int colq = (warp - 2) >> 2;          // 32-column slice of the 128-column tile handled by this warp
     const bool store_pre = p.act && p.pre;
     const int r = q * 32 + lane;               // row of the tile owned by this thread
-    uint8_t* so = stage_out + colhalf * OUT_HALF_BYTES + r * 128;
-    uint8_t* sp = stage_pre + colhalf * OUT_HALF_BYTES + r * 128;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      uint8_t* stage_out = stage_base + as * 2 * OUT_TILE_BYTES;
+      uint8_t* stage_pre = stage_out + OUT_TILE_BYTES;
+      uint8_t* so = stage_out + (colq >> 1) * OUT_HALF_BYTES + r * 128;
+      uint8_t* sp = stage_pre + (colq >> 1) * OUT_HALF_BYTES + r * 128;
       mbar_wait(&tmem_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      uint32_t v0[32], v1[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + colhalf * 64);
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32, v1);
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + colq * 32), v);
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       mbar_arrive(&tmem_empty[as]);  // accumulator drained into registers: the MMA warp may start the next-but-one tile
-      // the previous tile's TMA stores must have finished READING the staging tiles before they are overwritten
-      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      // the TMA stores issued two tiles ago (same staging buffer) must have finished READING it
+      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
       epi_bar();
 #pragma unroll
-      for (int j = 0; j < 8; j++) {  // 8 chunks of 8 columns = 16 B
-        const int cbase = n0 + colhalf * 64 + j * 8;
+      for (int j = 0; j < 4; j++) {  // 4 chunks of 8 columns = 16 B
+        const int cbase = n0 + colq * 32 + j * 8;
         float f[8], g[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-          const uint32_t raw = (j < 4) ? v0[(j & 3) * 8 + t] : v1[(j & 3) * 8 + t];
-          f[t] = __uint_as_float(raw) + ((p.bias && cbase + t < p.N) ? p.bias[cbase + t] : 0.f);
+          f[t] = __uint_as_float(v[j * 8 + t]) + ((p.bias && cbase + t < p.N) ? p.bias[cbase + t] : 0.f);
           g[t] = p.act ? gelu_erf(f[t]) : f[t];
         }
-        const int sw = (j ^ (r & 7)) * 16;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+        const int sw = (((colq & 1) * 4 + j) ^ (r & 7)) * 16;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
         *reinterpret_cast<bf16x8*>(so + sw) = pack8(g);
         if (store_pre) *reinterpret_cast<bf16x8*>(sp + sw) = pack8(f);
       }
@@ -318,7 +317,7 @@ ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bia
     return ESVIT_ERR_BAD_ARG;
   tg::Params p;
   p.out = (bf16*)out; p.pre = (bf16*)pre; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.act = act;
-  const size_t smem = (size_t)tg::STAGES * tg::STAGE_BYTES + 2 * tg::OUT_TILE_BYTES +
+  const size_t smem = (size_t)tg::STAGES * tg::STAGE_BYTES + 4 * tg::OUT_TILE_BYTES +
                       (2 * tg::STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
