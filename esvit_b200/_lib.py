@@ -33,6 +33,7 @@ SIGNATURES = {
     "esvit_gelu_fwd": [P, P, L, P],
     "esvit_gelu_bwd": [P, P, P, L, P],
     "esvit_gelu_bwd_dbias": [P, P, P, P, L, I, P],
+    "esvit_mul_bwd_dbias": [P, P, P, P, L, I, P],
     "esvit_l2norm_fwd": [P, P, P, F, L, I, P],
     "esvit_l2norm_bwd": [P, P, P, P, L, I, P],
     "esvit_weight_norm_fwd": [P, P, P, P, L, I, P],

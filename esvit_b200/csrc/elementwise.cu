@@ -86,6 +86,37 @@ __global__ void __launch_bounds__(256) gelu_bwd_dbias_kernel(const bf16* __restr
   if (blockIdx.x * 256 + tid < N) atomicAdd(&dbias[blockIdx.x * 256 + tid], a);
 }
 
+// dx = dy * gp (gp = stored local derivative, e.g. gelu'(pre) from the tcgen05 GEMM epilogue); dbias[col] += sum_rows dx.
+// Same tiling as gelu_bwd_dbias_kernel, but pure streaming: 6 B/element, no transcendental math.
+__global__ void __launch_bounds__(256) mul_bwd_dbias_kernel(const bf16* __restrict__ gp, const bf16* __restrict__ dy,
+                                                            bf16* __restrict__ dx, float* __restrict__ dbias,
+                                                            long long R, int N) {
+  __shared__ float sh[8][256 + 8];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < R; r += (long long)gridDim.y * 8) {
+      float f[8], g[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(gp + r * N + col), f);
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + r * N + col), g);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        g[j] *= f[j];
+        acc[j] += g[j];
+      }
+      *reinterpret_cast<bf16x8*>(dx + r * N + col) = pack8(g);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) sh[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  float a = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; y++) a += sh[y][tid];
+  if (blockIdx.x * 256 + tid < N) atomicAdd(&dbias[blockIdx.x * 256 + tid], a);
+}
+
 // one warp per row, D % 8 == 0, D <= 8*32*NV
 template <int NV>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
@@ -249,6 +280,20 @@ ESVIT_API int esvit_gelu_bwd_dbias(const void* x, const void* dy, void* dx, floa
   if (gy < 1) gy = 1;
   gelu_bwd_dbias_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
       (const bf16*)x, (const bf16*)dy, (bf16*)dx, dbias, R, N);
+  ESVIT_LAUNCH_CHECK();
+}
+
+// dx = dy * gp (bf16, [R, N]); dbias fp32 [N] = column sums of dx, ACCUMULATED (caller zero-fills)
+ESVIT_API int esvit_mul_bwd_dbias(const void* gp, const void* dy, void* dx, float* dbias, long long R, int N,
+                                  void* stream) {
+  if (N % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
+  const int gx = (N + 255) / 256;
+  long long gy = ((long long)esvit_num_sms() * 8 + gx - 1) / gx;
+  const long long maxgy = (R + 7) / 8;
+  if (gy > maxgy) gy = maxgy;
+  if (gy < 1) gy = 1;
+  mul_bwd_dbias_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      (const bf16*)gp, (const bf16*)dy, (bf16*)dx, dbias, R, N);
   ESVIT_LAUNCH_CHECK();
 }
 

@@ -115,7 +115,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {  // A&S 7.1.26, same polynomial as elementwise.cu
+// exact-erf GELU and its derivative from one exp (A&S 7.1.26 erf, same polynomial as elementwise.cu):
+// gelu(x) = x*Phi(x), gelu'(x) = Phi(x) + x*phi(x)
+__device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
   const float e = __expf(-0.5f * x * x);
   const float z = fabsf(x) * 0.70710678118654752f;
   const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
@@ -123,13 +125,14 @@ __device__ __forceinline__ float gelu_erf(float x) {  // A&S 7.1.26, same polyno
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float er = copysignf(1.f - p * t * e, x);
-  return 0.5f * x * (1.f + er);
+  const float cdf = 0.5f * (1.f + copysignf(1.f - p * t * e, x));
+  y = x * cdf;
+  dy = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 struct Params {
   bf16* out;        // [M, N] act(A W^T + bias)
-  bf16* pre;        // [M, N] pre-activation (A W^T + bias), written when act != 0 and pre != nullptr
+  bf16* pre;        // [M, N] d act/dx at the pre-activation (gelu'(A W^T + bias)), written when act != 0 and pre != nullptr
   const float* bias;  // [N] or nullptr
   int M, N, K, act;   // act: 0 = identity, 1 = exact GELU
 };
@@ -245,11 +248,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
 #pragma unroll
       for (int j = 0; j < 4; j++) {  // 4 chunks of 8 columns = 16 B
         const int cbase = n0 + colq * 32 + j * 8;
-        float f[8], g[8];
+        float f[8], g[8];  // g = act(x); f = what the `pre` slot receives: d act / dx (act = GELU), else unused
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-          f[t] = __uint_as_float(v[j * 8 + t]) + ((p.bias && cbase + t < p.N) ? p.bias[cbase + t] : 0.f);
-          g[t] = p.act ? gelu_erf(f[t]) : f[t];
+          const float x = __uint_as_float(v[j * 8 + t]) + ((p.bias && cbase + t < p.N) ? p.bias[cbase + t] : 0.f);
+          if (p.act) {
+            gelu_and_grad(x, g[t], f[t]);
+          } else {
+            g[t] = x;
+            f[t] = x;
+          }
         }
         const int sw = (((colq & 1) * 4 + j) ^ (r & 7)) * 16;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
         *reinterpret_cast<bf16x8*>(so + sw) = pack8(g);
@@ -307,7 +315,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long lon
 }  // namespace tg
 
 // out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]);  act: 0 identity, 1 exact GELU (then `pre`, if not NULL, receives
-// the pre-activation).  a, w bf16 row-major with K contiguous (K % 8 == 0, N % 8 == 0), bias fp32 or NULL.
+// gelu'(pre-activation), the local derivative the backward multiplies with).  a, w bf16 row-major with K contiguous (K % 8 == 0, N % 8 == 0), bias fp32 or NULL.
 ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M,
                                   int N, int K, int act, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8) || M > 0x7fffffffLL) return ESVIT_ERR_BAD_ARG;

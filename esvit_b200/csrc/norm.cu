@@ -32,52 +32,64 @@ template <> struct Vec4IO<bf16> {
 __device__ __forceinline__ float sum4(float4 v) { return (v.x + v.y) + (v.z + v.w); }
 
 // ---------------------------------------------------------------------------------------------
+// Row kernels.  LPR lanes share one row (8 / 16 / 32 by row width), so a warp streams 32/LPR rows at once: narrow rows
+// (C = 96 is the largest token count of the model) keep all lanes busy and 4x the bytes in flight per warp.
+// Lane l of its group owns float4 chunks (i*LPR + l), i < NV.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // forward: xout = x + keep[b] * delta ; y = LN(xout) * gamma + beta
-template <int NV, typename OutT>
+template <int LPR, int NV, typename OutT>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
     const float* __restrict__ x, const bf16* __restrict__ delta,
     const float* __restrict__ keep, int tokens_per_sample, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, float* __restrict__ xout, OutT* __restrict__ y,
     float* __restrict__ mean_o, float* __restrict__ rstd_o, long long T, int C) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float invC = 1.f / (float)C;
-  for (long long row = warp; row < T; row += nwarps) {
+  for (long long r0 = warp * RPW; r0 < T; r0 += nwarps * RPW) {
+    const long long row = r0 + sub;
+    const bool ok = row < T;
     float4 v[NV];
-    const float ks = keep ? keep[row / tokens_per_sample] : 1.f;
+    const float ks = (keep && ok) ? keep[row / tokens_per_sample] : 1.f;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) {
+      const int c = (i * LPR + l) * 4;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && c < C) {
         v[i] = Vec4IO<float>::ld(x + row * C + c);
         if (delta) {
-          float4 d = Vec4IO<bf16>::ld(delta + row * C + c);
+          const float4 d = Vec4IO<bf16>::ld(delta + row * C + c);
           v[i].x += ks * d.x; v[i].y += ks * d.y; v[i].z += ks * d.z; v[i].w += ks * d.w;
           if (xout) Vec4IO<float>::st(xout + row * C + c, v[i]);
         }
         s += sum4(v[i]);
-      } else {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (!y) continue;
-    const float mean = warp_sum(s) * invC;
+    const float mean = group_sum<LPR>(s) * invC;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-      const int c = (i * 32 + lane) * 4;
+      const int c = (i * LPR + l) * 4;
       if (c < C) {
         float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
         q += (a * a + b * b) + (cc * cc + d * d);
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+    const float rstd = rsqrtf(group_sum<LPR>(q) * invC + eps);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) {
+      const int c = (i * LPR + l) * 4;
+      if (ok && c < C) {
         float4 g = Vec4IO<float>::ld(gamma + c), b = Vec4IO<float>::ld(beta + c), o;
         o.x = (v[i].x - mean) * rstd * g.x + b.x;
         o.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -86,19 +98,20 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
         Vec4IO<OutT>::st(y + row * C + c, o);
       }
     }
-    if (lane == 0) { mean_o[row] = mean; rstd_o[row] = rstd; }
+    if (ok && l == 0) { mean_o[row] = mean; rstd_o[row] = rstd; }
   }
 }
 
-// backward: G = dxo + LNbwd(dy) ; dx = G ; ddelta = keep * G ; dgamma += dy*xhat ; dbeta += dy
-template <int NV, typename DyT>
-__global__ void __launch_bounds__(NV <= 2 ? 256 : 128, (NV <= 2 ? 2 : (NV <= 4 ? 4 : (NV <= 8 ? 2 : 1)))) add_ln_bwd_kernel(
+// backward: G = dxo + LNbwd(dy) ; dx = G ; ddelta = keep * G ; dgamma += dy*xhat ; dbeta += dy ; ddbias += keep*G
+template <int LPR, int NV, typename DyT>
+__global__ void __launch_bounds__(NV <= 4 ? 256 : 128) add_ln_bwd_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ dxo, const float* __restrict__ xs,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
     const float* __restrict__ keep, int tokens_per_sample, float* __restrict__ dx, bf16* __restrict__ ddelta,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ ddbias, long long T, int C) {
   extern __shared__ float sred[];  // [3*C]
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float invC = 1.f / (float)C;
@@ -109,17 +122,21 @@ __global__ void __launch_bounds__(NV <= 2 ? 256 : 128, (NV <= 2 ? 2 : (NV <= 4 ?
   }
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
-  for (long long row = warp; row < T; row += nwarps) {
-    const float ks = keep ? keep[row / tokens_per_sample] : 1.f;
+  for (long long r0 = warp * RPW; r0 < T; r0 += nwarps * RPW) {
+    const long long row = r0 + sub;
+    const bool ok = row < T;
+    const float ks = (keep && ok) ? keep[row / tokens_per_sample] : 1.f;
     float4 G[NV];
     if (dy) {
-      const float mean = mean_i[row], rstd = rstd_i[row];
+      const float mean = ok ? mean_i[row] : 0.f, rstd = ok ? rstd_i[row] : 0.f;
       float4 xh[NV], g[NV];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < C) {
+        const int c = (i * LPR + l) * 4;
+        xh[i] = make_float4(0, 0, 0, 0);
+        g[i] = make_float4(0, 0, 0, 0);
+        if (ok && c < C) {
           float4 xv = Vec4IO<float>::ld(xs + row * C + c);
           float4 d = Vec4IO<DyT>::ld(dy + row * C + c);
           float4 gm = Vec4IO<float>::ld(gamma + c);
@@ -131,17 +148,14 @@ __global__ void __launch_bounds__(NV <= 2 ? 256 : 128, (NV <= 2 ? 2 : (NV <= 4 ?
           ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
         }
       }
-      s1 = warp_sum(s1) * invC;
-      s2 = warp_sum(s2) * invC;
+      s1 = group_sum<LPR>(s1) * invC;
+      s2 = group_sum<LPR>(s2) * invC;
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < C) {
-          G[i].x = rstd * (g[i].x - s1 - xh[i].x * s2);
-          G[i].y = rstd * (g[i].y - s1 - xh[i].y * s2);
-          G[i].z = rstd * (g[i].z - s1 - xh[i].z * s2);
-          G[i].w = rstd * (g[i].w - s1 - xh[i].w * s2);
-        }
+        G[i].x = rstd * (g[i].x - s1 - xh[i].x * s2);
+        G[i].y = rstd * (g[i].y - s1 - xh[i].y * s2);
+        G[i].z = rstd * (g[i].z - s1 - xh[i].z * s2);
+        G[i].w = rstd * (g[i].w - s1 - xh[i].w * s2);
       }
     } else {
 #pragma unroll
@@ -149,8 +163,8 @@ __global__ void __launch_bounds__(NV <= 2 ? 256 : 128, (NV <= 2 ? 2 : (NV <= 4 ?
     }
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) {
+      const int c = (i * LPR + l) * 4;
+      if (ok && c < C) {
         if (dxo) {
           float4 o = Vec4IO<float>::ld(dxo + row * C + c);
           G[i].x += o.x; G[i].y += o.y; G[i].z += o.z; G[i].w += o.w;
@@ -162,23 +176,17 @@ __global__ void __launch_bounds__(NV <= 2 ? 256 : 128, (NV <= 2 ? 2 : (NV <= 4 ?
       }
     }
   }
-  if (dy) {
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) {
+  for (int i = 0; i < NV; i++) {
+    const int c = (i * LPR + l) * 4;
+    if (c < C) {
+      if (dy) {
         atomicAdd(&sred[c + 0], ag[i].x); atomicAdd(&sred[c + 1], ag[i].y);
         atomicAdd(&sred[c + 2], ag[i].z); atomicAdd(&sred[c + 3], ag[i].w);
         atomicAdd(&sred[C + c + 0], ab[i].x); atomicAdd(&sred[C + c + 1], ab[i].y);
         atomicAdd(&sred[C + c + 2], ab[i].z); atomicAdd(&sred[C + c + 3], ab[i].w);
       }
-    }
-  }
-  if (ddbias) {
-#pragma unroll
-    for (int i = 0; i < NV; i++) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) {
+      if (ddbias) {
         atomicAdd(&sred[2 * C + c + 0], ad[i].x); atomicAdd(&sred[2 * C + c + 1], ad[i].y);
         atomicAdd(&sred[2 * C + c + 2], ad[i].z); atomicAdd(&sred[2 * C + c + 3], ad[i].w);
       }
@@ -362,23 +370,42 @@ int row_grid(long long T, int warps_per_block, int waves) {
   else if ((C_) <= 2048) { CALL(16) }          \
   else return ESVIT_ERR_BAD_ARG;
 
+// (lanes per row, float4 chunks per lane) for a row of C floats
+static bool addln_shape(int C, int& lpr, int& nv) {
+  if (C % 4 != 0 || C <= 0 || C > 2048) return false;
+  const int c4 = C / 4;
+  lpr = c4 <= 32 ? 8 : (c4 <= 64 ? 16 : 32);
+  nv = (c4 + lpr - 1) / lpr;
+  if (nv == 5) nv = 6;
+  else if (nv == 7) nv = 8;
+  else if (nv > 8 && nv <= 12) nv = 12;
+  else if (nv > 12) nv = 16;
+  return true;
+}
+
+#define ADDLN_COMBOS(X) X(8, 1) X(8, 2) X(8, 3) X(8, 4) X(16, 3) X(16, 4) X(32, 3) X(32, 4) X(32, 6) X(32, 8) X(32, 12) X(32, 16)
+
 ESVIT_API int esvit_add_ln_fwd(const float* x, const void* delta, const float* keep, int tokens_per_sample,
                                const float* gamma, const float* beta, float eps, float* xout, void* y,
                                int y_is_bf16, float* mean, float* rstd, long long T, int C, void* stream) {
-  if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
+  int lpr, nv;
+  if (T <= 0 || !addln_shape(C, lpr, nv)) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = row_grid(T, 8, 8);
-#define CALL(NV)                                                                                              \
-  if (y_is_bf16)                                                                                              \
-    add_ln_fwd_kernel<NV, bf16><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep,                            \
-                                                      tokens_per_sample, gamma, beta, eps, xout, (bf16*)y,    \
-                                                      mean, rstd, T, C);                                      \
-  else                                                                                                        \
-    add_ln_fwd_kernel<NV, float><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep,                           \
-                                                       tokens_per_sample, gamma, beta, eps, xout, (float*)y,  \
-                                                       mean, rstd, T, C);
-  DISPATCH_NV(C, CALL)
-#undef CALL
+  const int grid = row_grid((T + 32 / lpr - 1) / (32 / lpr), 8, 8);
+  bool done = false;
+#define X(L, N)                                                                                                  \
+  if (!done && lpr == L && nv == N) {                                                                            \
+    done = true;                                                                                                 \
+    if (y_is_bf16)                                                                                               \
+      add_ln_fwd_kernel<L, N, bf16><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep, tokens_per_sample, gamma, \
+                                                          beta, eps, xout, (bf16*)y, mean, rstd, T, C);          \
+    else                                                                                                         \
+      add_ln_fwd_kernel<L, N, float><<<grid, 256, 0, st>>>(x, (const bf16*)delta, keep, tokens_per_sample,      \
+                                                           gamma, beta, eps, xout, (float*)y, mean, rstd, T, C); \
+  }
+  ADDLN_COMBOS(X)
+#undef X
+  if (!done) return ESVIT_ERR_BAD_ARG;
   ESVIT_LAUNCH_CHECK();
 }
 
@@ -386,22 +413,30 @@ ESVIT_API int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo,
                                const float* rstd, const float* gamma, const float* keep, int tokens_per_sample,
                                float* dx, void* ddelta, float* dgamma, float* dbeta, float* ddelta_bias, long long T,
                                int C, void* stream) {
-  if (C % 4 != 0 || T <= 0) return ESVIT_ERR_BAD_ARG;
+  int lpr, nv;
+  if (T <= 0 || !addln_shape(C, lpr, nv)) return ESVIT_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  // wide rows: 128-thread CTAs (the per-lane accumulators cost registers, not warps); narrow rows: fewer, larger CTAs
-  // (every CTA ends with 3*C global atomics - thousands of CTAs on a 96-wide row would serialise on them)
-  const int threads = C <= 256 ? 256 : 128;
-  const int grid = C <= 256 ? row_grid(T, 8, 4) : row_grid(T, 4, 16);
+  const int threads = nv <= 4 ? 256 : 128;
+  const long long warp_rows = (T + 32 / lpr - 1) / (32 / lpr);
+  // every CTA ends with 3*C global atomics: keep the CTA count modest
+  const int grid = row_grid(warp_rows, threads / 32, threads == 256 ? 4 : 8);
   const size_t smem = 3 * (size_t)C * sizeof(float);
-#define CALL(NV)                                                                                               \
-  if (dy_is_bf16)                                                                                              \
-    add_ln_bwd_kernel<NV, bf16><<<grid, threads, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,    \
-                                                         tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C); \
-  else                                                                                                         \
-    add_ln_bwd_kernel<NV, float><<<grid, threads, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma, keep,  \
-                                                          tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, ddelta_bias, T, C);
-  DISPATCH_NV(C, CALL)
-#undef CALL
+  bool done = false;
+#define X(L, N)                                                                                                      \
+  if (!done && lpr == L && nv == N) {                                                                                \
+    done = true;                                                                                                     \
+    if (dy_is_bf16)                                                                                                  \
+      add_ln_bwd_kernel<L, N, bf16><<<grid, threads, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,  \
+                                                                 tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, \
+                                                                 ddelta_bias, T, C);                                 \
+    else                                                                                                             \
+      add_ln_bwd_kernel<L, N, float><<<grid, threads, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma,      \
+                                                                  keep, tokens_per_sample, dx, (bf16*)ddelta, dgamma, \
+                                                                  dbeta, ddelta_bias, T, C);                         \
+  }
+  ADDLN_COMBOS(X)
+#undef X
+  if (!done) return ESVIT_ERR_BAD_ARG;
   ESVIT_LAUNCH_CHECK();
 }
 

@@ -326,7 +326,7 @@ class BiasGeluFn(Function):
 
 
 def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, want_pre: bool = False):
-    """tcgen05/TMA GEMM: act(a @ w^T + bias) -> bf16 [M, N] (and the pre-activation when act != 0 and want_pre)."""
+    """tcgen05/TMA GEMM: act(a @ w^T + bias) -> bf16 [M, N] (and gelu'(a @ w^T + bias) when act != 0 and want_pre)."""
     a, w = _chk(a, BF16, "a"), _chk(w, BF16, "w")
     bias = _chk(bias, F32, "bias")
     K = a.shape[-1]
@@ -340,8 +340,9 @@ def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, wa
 
 class LinearGeluFn(Function):
     """gelu(x @ w^T + b) as ONE tcgen05/TMA kernel (esvit_gemm_bias_act): the GEMM epilogue adds the bias, applies the
-    exact GELU and also stores the pre-activation, so the [T, 4C] hidden tensor is written once and never re-read in
-    the forward.  Backward: GELU' + bias gradient in one kernel, then dx / dw as library GEMMs."""
+    exact GELU and also emits gelu'(pre-activation), so the [T, 4C] hidden tensor is written once and never re-read in
+    the forward and the backward's dh = dy * gelu' (+ bias gradient) is a pure streaming kernel; dx / dw are library
+    GEMMs."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
@@ -353,12 +354,12 @@ class LinearGeluFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, w, pre = ctx.saved_tensors
+        x, w, pre = ctx.saved_tensors  # pre = gelu'(x @ w^T + b)
         g = _chk(g, BF16, "g")
         N = pre.shape[-1]
         dh = torch.empty_like(pre)
         db = torch.zeros(ctx.bias_meta[0], dtype=F32, device=ctx.bias_meta[1])
-        _lib.call("esvit_gelu_bwd_dbias", _p(pre), _p(g), _p(dh), _p(db), pre.numel() // N, N, _stream())
+        _lib.call("esvit_mul_bwd_dbias", _p(pre), _p(g), _p(dh), _p(db), pre.numel() // N, N, _stream())
         dh2 = dh.reshape(-1, N)
         dx = (dh2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
         dw = dh2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None

@@ -70,8 +70,8 @@ int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bi
                           int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
 
 /* ---- tcgen05 / TMA GEMM with fused epilogue ------------------------- nn.Linear + Mlp.act, models/swin_transformer.py:31-33
- * out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]); act 0 = identity, 1 = exact GELU (then `pre`, if not NULL, gets the
- * pre-activation the backward needs).  a, w bf16 row-major (K contiguous), K % 8 == 0, N % 8 == 0, bias fp32 or NULL.
+ * out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]); act 0 = identity, 1 = exact GELU (then `pre`, if not NULL, gets
+ * gelu'(pre-activation): the backward is dh = dy * pre, see esvit_mul_bwd_dbias).  a, w bf16 row-major (K contiguous), K % 8 == 0, N % 8 == 0, bias fp32 or NULL.
  * TMA-staged 128B-swizzled tiles, tcgen05.mma with the fp32 accumulator in TMEM, persistent over output tiles. */
 int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M, int N, int K,
                         int act, void* stream);
@@ -82,6 +82,8 @@ int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* s
 /* gelu backward that also ACCUMULATES dbias fp32 [N] = column sums of dx for x bf16 [R,N]: the gradient of the fc1
  * bias (added by the GEMM epilogue) without a separate reduction kernel. */
 int esvit_gelu_bwd_dbias(const void* x, const void* dy, void* dx, float* dbias, long long R, int N, void* stream);
+/* dx = dy * gp (gp = stored local derivative, bf16 [R,N]); ACCUMULATES dbias fp32 [N] = column sums of dx. */
+int esvit_mul_bwd_dbias(const void* gp, const void* dy, void* dx, float* dbias, long long R, int N, void* stream);
 
 /* ---- DINOHead pieces ------------------------------------------------------ models/vision_transformer.py:403-417
  * l2norm: y = x / max(||x||, eps) rows (bf16); weight_norm: w(bf16) = v * g / ||v||_row (fp32 v [K,D], g [K]). */

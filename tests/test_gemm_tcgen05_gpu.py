@@ -22,8 +22,10 @@ def test_gemm_bias_act(M, K, N, act):
     ref_pre = a.float() @ w.float().t() + b
     ref = F.gelu(ref_pre) if act else ref_pre
     if act:
-        out, pre = ops.gemm_bias_act(a, w, b, act=1, want_pre=True)
-        assert_close(pre, ref_pre, 5e-3, "pre-activation")
+        out, gp = ops.gemm_bias_act(a, w, b, act=1, want_pre=True)
+        xr = ref_pre.clone().requires_grad_(True)
+        F.gelu(xr).sum().backward()
+        assert_close(gp, xr.grad, 5e-3, "gelu'(pre-activation)")
     else:
         out = ops.gemm_bias_act(a, w, b, act=0)
     torch.cuda.synchronize()
