@@ -397,10 +397,11 @@ static cudaError_t opt_in_smem(K kernel, size_t smem) {
 }  // namespace wa
 
 // qkv bf16 [B,H,W,3C] = qkv GEMM output INCLUDING its bias (channel order [q|k|v][head][32]); qkv_bias bf16 [3C] is
-// what a padded slot holds; bias_table fp32 [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32 [B*nW, nH, ws*ws]
-ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, void* out,
-                                    float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
-                                    void* stream) {
+// what a padded slot holds; bias_table fp32 [(2ws-1)^2, nH]; bias_ws fp32 [nH*4096] workspace (expanded bias, ws=7
+// path); out bf16 [B,H,W,C]; lse fp32 [B*nW, nH, ws*ws]
+ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws,
+                                    void* out, float* lse, int B, int H, int W, int C, int nH, int ws, int shift,
+                                    float scale, void* stream) {
   wa::Geo g;
   if (!wa::make_geo(g, B, H, W, C, nH, ws, shift)) return ESVIT_ERR_BAD_ARG;
   const int nwin = B * g.nWy * g.nWx;
@@ -408,13 +409,15 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
   const bf16* q = (const bf16*)qkv;
   const bf16* qb = (const bf16*)qkv_bias;
   if (ws == 7) {
+    if (!bias_ws) return ESVIT_ERR_BAD_ARG;
+    wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
     const size_t smem = wa::fwd7_smem();
     int gx = (esvit_num_sms() * 16 + nH - 1) / nH;  // persistent: ~4 waves of 4 resident CTAs per SM
     if (gx > nwin) gx = nwin;
     if (shift > 0)
-      wa::window_attn_fwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_table, (bf16*)out, lse, g, scale, nwin);
+      wa::window_attn_fwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
     else
-      wa::window_attn_fwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_table, (bf16*)out, lse, g, scale, nwin);
+      wa::window_attn_fwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
   } else {
     const size_t smem = wa::fwd_smem<14>();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_fwd_kernel<14>, smem);
@@ -428,10 +431,10 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
 // dqkv bf16 [B,H,W,3C] is fully written; dbias_table fp32 [(2ws-1)^2, nH] and dqkv_bias fp32 [3C] (the COMPLETE
 // qkv-bias gradient: column sums of dq/dk/dv over all window slots, padded ones included) are ACCUMULATED into
 // (caller zero-fills).
-ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, const void* out,
-                                    const void* dout, const float* lse, void* dqkv, float* dbias_table,
-                                    float* dqkv_bias, int B, int H, int W, int C, int nH, int ws, int shift,
-                                    float scale, void* stream) {
+ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws,
+                                    const void* out, const void* dout, const float* lse, void* dqkv,
+                                    float* dbias_table, float* dqkv_bias, int B, int H, int W, int C, int nH, int ws,
+                                    int shift, float scale, void* stream) {
   wa::Geo g;
   if (!wa::make_geo(g, B, H, W, C, nH, ws, shift)) return ESVIT_ERR_BAD_ARG;
   const int nwin = B * g.nWy * g.nWx;
@@ -439,6 +442,8 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
   const bf16* q = (const bf16*)qkv;
   const bf16* qb = (const bf16*)qkv_bias;
   if (ws == 7) {
+    if (!bias_ws) return ESVIT_ERR_BAD_ARG;
+    wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
     const size_t smem = wa::bwd7_smem();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<true>, smem);
     if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<false>, smem);
@@ -446,11 +451,11 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
     int gx = (esvit_num_sms() * 12 + nH - 1) / nH;  // 3 CTAs / SM resident, ~4 waves of persistent CTAs
     if (gx > nwin) gx = nwin;
     if (shift > 0)
-      wa::window_attn_bwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_table, (const bf16*)out,
+      wa::window_attn_bwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                          (const bf16*)dout, lse, (bf16*)dqkv,
                                                                          dbias_table, dqkv_bias, g, scale, nwin);
     else
-      wa::window_attn_bwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_table, (const bf16*)out,
+      wa::window_attn_bwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                           (const bf16*)dout, lse, (bf16*)dqkv,
                                                                           dbias_table, dqkv_bias, g, scale, nwin);
   } else {

@@ -19,6 +19,20 @@ namespace wa {
 constexpr int BLD = 72;        // row stride (floats) of the expanded bias table: 72 % 32 == 8 -> conflict-free float2 reads
 constexpr int TILE7 = 64 * LD;  // bf16 elements of one 64-row tile
 
+// Rel-pos bias of every head expanded ONCE per call to a dense [nH][64][64] fp32 table in the log2 domain with -inf in
+// the padded rows/columns (it doubles as the key-padding mask).  The first versions expanded it in every CTA's
+// prologue: ~3700 instructions per warp of index arithmetic, more than the whole attention loop of a late stage.
+__global__ void __launch_bounds__(256) expand_bias7_kernel(const float* __restrict__ bias_table, float* __restrict__ bexp,
+                                                           int nH) {
+  const int h = blockIdx.x;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int row = i >> 6, col = i & 63;
+    float v = -INFINITY;
+    if (col < 49) v = row < 49 ? bias_table[bias_index<7>(row, col) * nH + h] * LOG2E : 0.f;
+    bexp[(long long)h * 4096 + i] = v;
+  }
+}
+
 // Issue the async gathers of one window into a pipeline stage: tiles [Q | K | V] (+ [dO | O] and lse for BWD).
 template <bool BWD>
 __device__ __forceinline__ void issue7(const Geo& g, int win, int h, const bf16* __restrict__ qkv,
@@ -57,7 +71,7 @@ __device__ __forceinline__ void issue7(const Geo& g, int win, int h, const bf16*
 // ------------------------------------------------------------------------------------------------
 template <bool SHIFT>
 __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
-    const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bias_table,
+    const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
     bf16* __restrict__ out, float* __restrict__ lse, Geo g, float scale, int nwin_total) {
   constexpr int WS = 7;
   using C = Cfg<WS>;
@@ -74,18 +88,17 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
   if (win < nwin_total) issue7<false>(g, win, h, qkv, qkv_bias, nullptr, nullptr, nullptr, tiles, nullptr, tokb, ridb);
   cp_async_commit();
 
-  // rel-pos bias of (head h, this warp's 16 query rows) in accumulator-fragment layout, log2 domain
+  // rel-pos bias of (head h, this warp's 16 query rows) in accumulator-fragment layout, from the expanded table
   float breg[C::NT8][4];
+  {
+    const float* bh = bexp + (long long)h * 4096 + (lane & 3) * 2;
 #pragma unroll
-  for (int nt = 0; nt < C::NT8; nt++)
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int row = (e < 2) ? rA : rB, col = nt * 8 + (lane & 3) * 2 + (e & 1);
-      float v = 0.f;
-      if (col >= C::NT) v = -INFINITY;
-      else if (row < C::NT) v = bias_table[bias_index<WS>(row, col) * g.nH + h] * LOG2E;
-      breg[nt][e] = v;
+    for (int nt = 0; nt < C::NT8; nt++) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(bh + rA * 64 + nt * 8));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bh + rB * 64 + nt * 8));
+      breg[nt][0] = a.x; breg[nt][1] = a.y; breg[nt][2] = b.x; breg[nt][3] = b.y;
     }
+  }
   const float c = scale * LOG2E;
   const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
 
@@ -195,7 +208,7 @@ static size_t fwd7_smem() { return (size_t)2 * 3 * TILE7 * 2 + (size_t)4 * 64 * 
 // qkv-bias gradients are the column sums of dQ / dK / dV over all 49 slots (padded ones included).
 template <bool SHIFT>
 __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
-    const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bias_table,
+    const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
     int nwin_total) {
@@ -219,10 +232,11 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
   if (win < nwin_total) issue7<true>(g, win, h, qkv, qkv_bias, dout, out, lse, tiles, Lrawb, tokb, ridb);
   cp_async_commit();
 
-  for (int i = threadIdx.x; i < C::KP * C::KP; i += NTHREADS) {
-    const int row = i >> 6, col = i & 63;
-    bm[row * BLD + col] = (row < C::NT && col < C::NT) ? bias_table[bias_index<WS>(row, col) * g.nH + h] * LOG2E
-                                                       : -INFINITY;
+  for (int i = threadIdx.x; i < C::KP * C::KP / 4; i += NTHREADS) {  // copy the expanded table of head h (float4)
+    const int row = i >> 4, c4 = (i & 15) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(bexp + (long long)h * 4096 + row * 64 + c4));
+    if (row >= C::NT) v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // padded query rows: P = 0
+    *reinterpret_cast<float4*>(bm + row * BLD + c4) = v;
   }
   for (int i = threadIdx.x; i < C::NB; i += NTHREADS) dbt[i] = 0.f;
   for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) dqb[i] = 0.f;

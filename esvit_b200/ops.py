@@ -261,8 +261,9 @@ class WindowAttentionFn(Function):
         nwin = B * (-(-H // ws)) * (-(-W // ws))
         out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
         lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
-        _lib.call("esvit_window_attn_fwd", _p(qkv), _p(qb), _p(bias_table), _p(out), _p(lse), B, H, W, C, num_heads, ws,
-                  shift, scale, _stream())
+        bws = torch.empty(num_heads * 4096, dtype=F32, device=qkv.device)  # expanded rel-pos bias (kernel workspace)
+        _lib.call("esvit_window_attn_fwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(lse), B, H, W, C,
+                  num_heads, ws, shift, scale, _stream())
         ctx.save_for_backward(qkv, qb, bias_table, out, lse)
         ctx.geo = (B, H, W, C, num_heads, ws, shift, scale)
         return out
@@ -276,7 +277,8 @@ class WindowAttentionFn(Function):
         dqkv = torch.empty_like(qkv)
         dtable = torch.zeros_like(bias_table)
         dqb = torch.zeros(3 * C, dtype=F32, device=qkv.device)
-        _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(out), _p(g), _p(lse), _p(dqkv),
+        bws = torch.empty(nH * 4096, dtype=F32, device=qkv.device)
+        _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(g), _p(lse), _p(dqkv),
                   _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
         return dqkv, dqb, dtable, None, None, None, None, None, None
 

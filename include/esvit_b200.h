@@ -62,12 +62,14 @@ int esvit_patch_embed_bwd(const float* img, const float* w, const float* bias, c
  * qkv bf16 [B,H,W,3C] ([q|k|v][head][32]) is the qkv GEMM output including its bias; qkv_bias bf16 [3C] is what a
  * padded slot holds (the bias alone); bias_table fp32 [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32
  * [B*nWindows, nH, ws*ws].  ws in {7,14}; head_dim 32.
+ * bias_ws fp32 [nH*4096]: caller-owned workspace, receives the rel-pos bias expanded to [nH][64][64] (ws = 7 path).
  * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] (complete qkv-bias gradient) ACCUMULATED. */
-int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, void* out, float* lse,
-                          int B, int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
-int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, const void* out,
-                          const void* dout, const float* lse, void* dqkv, float* dbias_table, float* dqkv_bias, int B,
-                          int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
+int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws, void* out,
+                          float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
+int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws,
+                          const void* out, const void* dout, const float* lse, void* dqkv, float* dbias_table,
+                          float* dqkv_bias, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
+                          void* stream);
 
 /* ---- tcgen05 / TMA GEMM with fused epilogue ------------------------- nn.Linear + Mlp.act, models/swin_transformer.py:31-33
  * out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]); act 0 = identity, 1 = exact GELU (then `pre`, if not NULL, gets
