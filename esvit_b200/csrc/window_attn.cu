@@ -415,9 +415,9 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
     int gx = (esvit_num_sms() * 16 + nH - 1) / nH;  // persistent: ~4 waves of 4 resident CTAs per SM
     if (gx > nwin) gx = nwin;
     if (shift > 0)
-      wa::window_attn_fwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
+      wa::window_attn_fwd7_kernel<true><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
     else
-      wa::window_attn_fwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
+      wa::window_attn_fwd7_kernel<false><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
   } else {
     const size_t smem = wa::fwd_smem<14>();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_fwd_kernel<14>, smem);
@@ -451,11 +451,11 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
     int gx = (esvit_num_sms() * 12 + nH - 1) / nH;  // 3 CTAs / SM resident, ~4 waves of persistent CTAs
     if (gx > nwin) gx = nwin;
     if (shift > 0)
-      wa::window_attn_bwd7_kernel<true><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
+      wa::window_attn_bwd7_kernel<true><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                          (const bf16*)dout, lse, (bf16*)dqkv,
                                                                          dbias_table, dqkv_bias, g, scale, nwin);
     else
-      wa::window_attn_bwd7_kernel<false><<<dim3(gx, nH), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
+      wa::window_attn_bwd7_kernel<false><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                           (const bf16*)dout, lse, (bf16*)dqkv,
                                                                           dbias_table, dqkv_bias, g, scale, nwin);
   } else {

@@ -81,10 +81,10 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
   int* tokb = reinterpret_cast<int*>(tiles + 2 * 3 * TILE7);      // [2][64]
   int* ridb = tokb + 2 * 64;                                     // [2][64]
 
-  const int h = blockIdx.y;
+  const int h = blockIdx.x;  // heads fastest: the nH CTAs sharing a window's token rows run together (DRAM page locality)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = warp * 16, rA = r0 + (lane >> 2), rB = rA + 8;
-  int win = blockIdx.x, stage = 0;
+  int win = blockIdx.y, stage = 0;
   if (win < nwin_total) issue7<false>(g, win, h, qkv, qkv_bias, nullptr, nullptr, nullptr, tiles, nullptr, tokb, ridb);
   cp_async_commit();
 
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
   const float c = scale * LOG2E;
   const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
 
-  for (; win < nwin_total; win += gridDim.x, stage ^= 1) {
-    const int nxt = win + gridDim.x;
+  for (; win < nwin_total; win += gridDim.y, stage ^= 1) {
+    const int nxt = win + gridDim.y;
     if (nxt < nwin_total)
       issue7<false>(g, nxt, h, qkv, qkv_bias, nullptr, nullptr, nullptr, tiles + (stage ^ 1) * 3 * TILE7, nullptr,
                     tokb + (stage ^ 1) * 64, ridb + (stage ^ 1) * 64);
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
   int* tokb = reinterpret_cast<int*>(Lrawb + 2 * 64);                 // [2][64]
   int* ridb = tokb + 2 * 64;                                          // [2][64]
 
-  const int h = blockIdx.y;
+  const int h = blockIdx.x;  // heads fastest: the nH CTAs sharing a window's token rows run together (DRAM page locality)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int win = blockIdx.x, stage = 0;
+  int win = blockIdx.y, stage = 0;
   if (win < nwin_total) issue7<true>(g, win, h, qkv, qkv_bias, dout, out, lse, tiles, Lrawb, tokb, ridb);
   cp_async_commit();
 
@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
   const int rA = r0 + (lane >> 2), rB = rA + 8;
   const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;  // A-fragment rows of the tile
 
-  for (; win < nwin_total; win += gridDim.x, stage ^= 1) {
-    const int nxt = win + gridDim.x;
+  for (; win < nwin_total; win += gridDim.y, stage ^= 1) {
+    const int nxt = win + gridDim.y;
     if (nxt < nwin_total)
       issue7<true>(g, nxt, h, qkv, qkv_bias, dout, out, lse, tiles + (stage ^ 1) * 5 * TILE7, Lrawb + (stage ^ 1) * 64,
                    tokb + (stage ^ 1) * 64, ridb + (stage ^ 1) * 64);
