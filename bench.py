@@ -230,6 +230,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
@@ -253,7 +255,7 @@ def main():
     # ---- roofline of the dominant kernel: CUDA events around each launch, in EAGER steps (events cannot be
     # recorded inside a replayed graph); these steps double as the warm-up the graph capture needs -------------
     _lib.reset_counters()
-    _lib.time_entry_point("esvit_dino_ce_bwd")
+    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_window_attn_bwd", "esvit_window_attn_fwd", "esvit_gemm_bias_act"])
     n_eager = 3 if args.min_warmup >= 3 else 1
     for _ in range(n_eager):
         l = one_step(crops)
@@ -308,22 +310,37 @@ def main():
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    roofline = None
+    roofline, roofline_others = None, []
     if timed:
-        # algorithmic bytes of one region-row launch: read student rows + read each paired teacher row
-        # once + write the bf16 gradient rows.  Per image: (170 + 98 + 170) rows x K x 2 B  
+        def agg(name, bytes_fn, label, extra=None):
+            sel = [t for t in timed if t["name"] == name and (extra is None or extra(t))]
+            if not sel:
+                return None
+            ms = sum(t["ms"] for t in sel)
+            alg = sum(bytes_fn(t) for t in sel)
+            ach = alg / (ms / 1e3) / 1e9
+            return {"kernel": label, "timed_in": f"{n_eager} eager step(s) before the graph-replayed region (CUDA events per launch)",
+                    "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "launch_ms": ms / len(sel),
+                    "algorithmic_bytes": alg / len(sel), "launches_timed": len(sel), "ms_per_step": ms / n_eager}
         Tg, Tl = 49, 9
         rows_s = B * (2 * Tg + n_local * Tl)
         rows_t = B * 2 * Tg
-        big = [t for t in timed if t["rows"] == rows_s]
-        if big:
-            avg_ms = sum(t["ms"] for t in big) / len(big)
-            alg = (2 * rows_s + rows_t) * args.out_dim * 2
-            ach = alg / (avg_ms / 1e3) / 1e9
-            roofline = {"kernel": "dino_ce_bwd_kernel (region rows)", "timed_in": "3 eager steps before the graph-replayed region",
-                    "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                        "peak_source": peak_src, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                        "launch_ms": avg_ms, "algorithmic_bytes": alg, "launches_timed": len(big)}
+        # attention backward (the largest of this repo's kernels by time): reads qkv (6C) + dO (2C) + O (2C), writes dqkv
+        # (6C) bytes per token -> 16*C per token; forward: 8*C per token
+        r_bwd = agg("esvit_window_attn_bwd", lambda t: 16 * t["tokens"] * t["C"], "window_attn_bwd7_kernel (all launches of a step)")
+        r_fwd = agg("esvit_window_attn_fwd", lambda t: 8 * t["tokens"] * t["C"], "window_attn_fwd7_kernel (all launches of a step)")
+        # region-row CE backward: read student rows + each paired teacher row once + write bf16 grads:
+        # (170 + 98 + 170) rows x K x 2 B per image
+        r_ce = agg("esvit_dino_ce_bwd", lambda t: (2 * rows_s + rows_t) * t["K"] * 2, "dino_ce_bwd_kernel (region rows)",
+                   extra=lambda t: t["rows"] == rows_s)
+        # tcgen05 fc1 GEMM + bias + GELU: reads A (M*K) and W, writes out and gelu' (2*M*N) in bf16
+        r_gemm = agg("esvit_gemm_bias_act", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
+                     "tg::gemm_bias_act_kernel tcgen05 fc1+bias+GELU (all launches of a step)")
+        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm) if r]
+        if cands:
+            cands.sort(key=lambda r: -r["ms_per_step"])
+            roofline, roofline_others = cands[0], cands[1:]
 
     if args.profile and rank == 0:
         step.use_cuda_graph = False
@@ -353,7 +370,7 @@ def main():
                           "optimizer": "esvit fused clip+AdamW+EMA" if args.optimizer == "fused" else "torch AdamW fused",
                           "cuda_graph": use_graph,
                           "l2": "per-step working set (>10 GB of activations/logits) >> 126 MB L2; no explicit flush"},
-               "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+               "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_others": roofline_others,
                "cpu_baseline": cpu_baseline, "loss": float(l)}
         print(json.dumps(out), flush=True)
     # Hard exit on every rank: tearing the NCCL communicator down while CUDA graphs that captured collectives are

@@ -101,9 +101,15 @@ def call(name: str, *args) -> None:
 # kernels launched per call of each entry point (entries that launch more than one kernel are computed per call)
 _LAUNCHES = {"esvit_colsum": 2, "esvit_window_attn_fwd": 2, "esvit_window_attn_bwd": 2}  # (+ bias expansion)
 _launch_count = 0
-_timed_name = None
+_timed_names = set()
 _timed_events = []
-_ROWS_ARG = {"esvit_dino_ce_bwd": -3, "esvit_dino_ce_fwd": -3, "esvit_row_lse": -3}
+# algorithmic-bytes meta per timed entry point (bench.py roofline): extracted from the call's own arguments
+_META = {
+    "esvit_dino_ce_bwd": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
+    "esvit_window_attn_bwd": lambda a: {"tokens": int(a[-9]) * int(a[-8]) * int(a[-7]), "C": int(a[-6])},
+    "esvit_window_attn_fwd": lambda a: {"tokens": int(a[-9]) * int(a[-8]) * int(a[-7]), "C": int(a[-6])},
+    "esvit_gemm_bias_act": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7])},
+}
 
 
 def reset_counters() -> None:
@@ -116,17 +122,24 @@ def launch_count() -> int:
     return _launch_count
 
 
-def time_entry_point(name) -> None:
-    """Bracket every call of `name` with CUDA events on the launching (current) stream."""
-    global _timed_name
-    _timed_name = name
+def time_entry_point(names) -> None:
+    """Bracket every call of the named entry point(s) with CUDA events on the launching (current) stream."""
+    global _timed_names
+    if names is None:
+        _timed_names = set()
+    elif isinstance(names, str):
+        _timed_names = {names}
+    else:
+        _timed_names = set(names)
 
 
 def timed_results():
-    """[{ms, rows}] of the timed entry point (call after a device synchronize)."""
+    """[{name, ms, ...meta}] of the timed entry points (call after a device synchronize)."""
     out = []
-    for e0, e1, rows in _timed_events:
-        out.append({"ms": e0.elapsed_time(e1), "rows": rows})
+    for name, e0, e1, meta in _timed_events:
+        d = {"name": name, "ms": e0.elapsed_time(e1)}
+        d.update(meta)
+        out.append(d)
     return out
 
 
@@ -145,13 +158,12 @@ def call(name: str, *args) -> None:  # noqa: F811  (instrumented wrapper)
         _launch_count += (args[8] + 31) // 32 + 1
     else:
         _launch_count += _LAUNCHES.get(name, 1)
-    if name == _timed_name:
+    if name in _timed_names:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _plain_call(name, *args)
         e1.record()
-        rows = int(args[_ROWS_ARG[name]]) if name in _ROWS_ARG else 0
-        _timed_events.append((e0, e1, rows))
+        _timed_events.append((name, e0, e1, _META[name](args) if name in _META else {}))
     else:
         _plain_call(name, *args)
