@@ -11,6 +11,7 @@ constexpr int PLD = KC + 8;  // smem row stride of the P / dS chunk tiles
 
 struct Geo {
   int B, H, W, C, nH, shift, Hp, Wp, nWx, nWy;
+  int dbg;  // profiling aid (ESVIT_ATTN_DBG): 1 = gather only the first window per CTA, 2 = skip the math
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {

@@ -17,6 +17,8 @@
 // Math: bf16 mma.sync m16n8k16 with fp32 accumulate; softmax in fp32 registers; P rounded to bf16 for PV
 // (same as the reference under autocast).  head_dim is 32 in every Swin variant.
 // The backward recomputes P from the saved log-sum-exp (no [B_, nH, N, N] tensor is saved).
+#include <cstdlib>
+
 #include "wa_common.cuh"
 #include "window_attn7.cuh"
 
@@ -385,6 +387,8 @@ static bool make_geo(Geo& g, int B, int H, int W, int C, int nH, int ws, int shi
   g.Wp = (W + ws - 1) / ws * ws;
   g.nWy = g.Hp / ws;
   g.nWx = g.Wp / ws;
+  const char* d = getenv("ESVIT_ATTN_DBG");
+  g.dbg = d ? atoi(d) : 0;
   return true;
 }
 

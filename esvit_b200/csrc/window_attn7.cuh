@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
 
   for (; win < nwin_total; win += gridDim.y, stage ^= 1) {
     const int nxt = win + gridDim.y;
-    if (nxt < nwin_total)
+    if (nxt < nwin_total && g.dbg != 1)
       issue7<false>(g, nxt, h, qkv, qkv_bias, nullptr, nullptr, nullptr, tiles + (stage ^ 1) * 3 * TILE7, nullptr,
                     tokb + (stage ^ 1) * 64, ridb + (stage ^ 1) * 64);
     cp_async_commit();
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
     const bf16* Vs = Ks + TILE7;
     const int* tok = tokb + stage * 64;
     const int* rid = ridb + stage * 64;
+    if (g.dbg == 2) { __syncthreads(); continue; }
 
     uint32_t qa[2][4];
     ldsm_x4(qa[0], Qs + frag_off);
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
 
   for (; win < nwin_total; win += gridDim.y, stage ^= 1) {
     const int nxt = win + gridDim.y;
-    if (nxt < nwin_total)
+    if (nxt < nwin_total && g.dbg != 1)
       issue7<true>(g, nxt, h, qkv, qkv_bias, dout, out, lse, tiles + (stage ^ 1) * 5 * TILE7, Lrawb + (stage ^ 1) * 64,
                    tokb + (stage ^ 1) * 64, ridb + (stage ^ 1) * 64);
     cp_async_commit();
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
     const float* Lraw = Lrawb + stage * 64;
     const int* tok = tokb + stage * 64;
     const int* rid = ridb + stage * 64;
+    if (g.dbg == 2) { __syncthreads(); continue; }
     {  // D[t] = rowsum(dO * O): two threads per row
       const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
       float part = 0.f;
