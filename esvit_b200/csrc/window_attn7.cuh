@@ -34,9 +34,12 @@ __global__ void __launch_bounds__(256) expand_bias7_kernel(const float* __restri
 }
 
 // Issue the async gathers of one window into a pipeline stage: tiles [Q | K | V] (+ [dO | O] and lse for BWD).
-template <bool BWD>
+// Padded slots hold the qkv bias of this head: every thread keeps ITS three 16-byte bias chunks (q,k,v at its c16) in
+// registers and stores them to shared memory directly - gathering them from global memory made thousands of CTAs hammer
+// the same few cache lines (local crops: 5x slower gathers than global crops with the same window count).
+template <bool BWD, int NTHREADS = 128>
 __device__ __forceinline__ void issue7(const Geo& g, int win, int h, const bf16* __restrict__ qkv,
-                                       const bf16* __restrict__ qkv_bias, const bf16* __restrict__ dout,
+                                       const uint4 (&bchunk)[3], const bf16* __restrict__ dout,
                                        const bf16* __restrict__ out, const float* __restrict__ lse, bf16* tiles,
                                        float* Lraw, int* tok, int* rid) {
   constexpr int WS = 7, NT = 49;
@@ -45,18 +48,24 @@ __device__ __forceinline__ void issue7(const Geo& g, int win, int h, const bf16*
   // two slots for all of q, k, v (+ dO, O), so the slot geometry is computed twice per thread per window, not 6-10x.
   const int c16 = threadIdx.x & 3;
 #pragma unroll
-  for (int kk = 0; kk < 2; kk++) {
-    const int t = (threadIdx.x >> 2) + 32 * kk;
+  for (int kk = 0; kk < 256 / NTHREADS; kk++) {
+    const int t = (threadIdx.x >> 2) + (NTHREADS / 4) * kk;
     int tk = -1, r = 0;
     if (t < NT) slot_info<WS>(g, b, wy, wx, t, tk, r);
-    const bf16* src_row = (tk >= 0 ? qkv + (long long)tk * 3 * g.C : qkv_bias) + h * HD + c16 * 8;
-    const int nbytes = t < NT ? 16 : 0;  // slots >= 49: zero fill
+    const bf16* src_row = qkv + (long long)(tk >= 0 ? tk : 0) * 3 * g.C + h * HD + c16 * 8;
+    const int nbytes = (t < NT && g.dbg != 1) ? 16 : 0;  // slots >= 49: zero fill (dbg 1: no global reads at all)
+    if (t < NT && tk < 0) {
 #pragma unroll
-    for (int part = 0; part < 3; part++)
-      cp_async16(tiles + part * TILE7 + t * LD + c16 * 8, src_row + part * g.C, nbytes);
+      for (int part = 0; part < 3; part++)
+        *reinterpret_cast<uint4*>(tiles + part * TILE7 + t * LD + c16 * 8) = bchunk[part];
+    } else {
+#pragma unroll
+      for (int part = 0; part < 3; part++)
+        cp_async16(tiles + part * TILE7 + t * LD + c16 * 8, src_row + part * g.C, nbytes);
+    }
     if (BWD) {
       const long long off = (long long)(tk >= 0 ? tk : 0) * g.C + h * HD + c16 * 8;
-      const int nb = tk >= 0 ? 16 : 0;  // padded slots: their output is cropped -> dO = O = 0
+      const int nb = (tk >= 0 && g.dbg != 1) ? 16 : 0;  // padded slots: their output is cropped -> dO = O = 0
       cp_async16(tiles + 3 * TILE7 + t * LD + c16 * 8, dout + off, nb);
       cp_async16(tiles + 4 * TILE7 + t * LD + c16 * 8, out + off, nb);
     }
@@ -85,7 +94,11 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = warp * 16, rA = r0 + (lane >> 2), rB = rA + 8;
   int win = blockIdx.y, stage = 0;
-  if (win < nwin_total) issue7<false>(g, win, h, qkv, qkv_bias, nullptr, nullptr, nullptr, tiles, nullptr, tokb, ridb);
+  uint4 bchunk[3];
+#pragma unroll
+  for (int part = 0; part < 3; part++)
+    bchunk[part] = __ldg(reinterpret_cast<const uint4*>(qkv_bias + part * g.C + h * HD + (threadIdx.x & 3) * 8));
+  if (win < nwin_total) issue7<false>(g, win, h, qkv, bchunk, nullptr, nullptr, nullptr, tiles, nullptr, tokb, ridb);
   cp_async_commit();
 
   // rel-pos bias of (head h, this warp's 16 query rows) in accumulator-fragment layout, from the expanded table
@@ -104,8 +117,8 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
 
   for (; win < nwin_total; win += gridDim.y, stage ^= 1) {
     const int nxt = win + gridDim.y;
-    if (nxt < nwin_total && g.dbg != 1)
-      issue7<false>(g, nxt, h, qkv, qkv_bias, nullptr, nullptr, nullptr, tiles + (stage ^ 1) * 3 * TILE7, nullptr,
+    if (nxt < nwin_total)
+      issue7<false>(g, nxt, h, qkv, bchunk, nullptr, nullptr, nullptr, tiles + (stage ^ 1) * 3 * TILE7, nullptr,
                     tokb + (stage ^ 1) * 64, ridb + (stage ^ 1) * 64);
     cp_async_commit();
     cp_async_wait<1>();
@@ -208,15 +221,18 @@ static size_t fwd7_smem() { return (size_t)2 * 3 * TILE7 * 2 + (size_t)4 * 64 * 
 //                                   -> dV = P^T dO, dK = dS^T Q straight from the accumulator fragments
 // qkv-bias gradients are the column sums of dQ / dK / dV over all 49 slots (padded ones included).
 template <bool SHIFT>
-__global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
+__global__ void __launch_bounds__(256, 2) window_attn_bwd7_kernel(
     const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
     int nwin_total) {
   constexpr int WS = 7;
   using C = Cfg<WS>;
-  constexpr int NTHREADS = 128;
-  static_assert(C::KP == 64 && C::NW == 4, "fast path assumes a 64-slot window and 4 warps");
+  // 8 warps: warps 0-3 run phase A (one 16-query tile each), warps 4-7 run phase B (one 16-key tile each) of the SAME
+  // (window, head) concurrently - both phases only read the shared tiles, so the unit's latency is halved and the
+  // SM holds twice the warps for the same shared memory.
+  constexpr int NTHREADS = 256;
+  static_assert(C::KP == 64 && C::NW == 4, "fast path assumes a 64-slot window and 4 tiles per phase");
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* tiles = reinterpret_cast<bf16*>(smraw);                       // [2 stages][Q | K | V | dO | O]
   float* bm = reinterpret_cast<float*>(tiles + 2 * 5 * TILE7);         // [64][BLD] expanded bias (log2 domain, -inf pad)
@@ -230,7 +246,11 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
   const int h = blockIdx.x;  // heads fastest: the nH CTAs sharing a window's token rows run together (DRAM page locality)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int win = blockIdx.y, stage = 0;
-  if (win < nwin_total) issue7<true>(g, win, h, qkv, qkv_bias, dout, out, lse, tiles, Lrawb, tokb, ridb);
+  uint4 bchunk[3];
+#pragma unroll
+  for (int part = 0; part < 3; part++)
+    bchunk[part] = __ldg(reinterpret_cast<const uint4*>(qkv_bias + part * g.C + h * HD + (threadIdx.x & 3) * 8));
+  if (win < nwin_total) issue7<true, NTHREADS>(g, win, h, qkv, bchunk, dout, out, lse, tiles, Lrawb, tokb, ridb);
   cp_async_commit();
 
   for (int i = threadIdx.x; i < C::KP * C::KP / 4; i += NTHREADS) {  // copy the expanded table of head h (float4)
@@ -246,14 +266,15 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
   for (int nt = 0; nt < C::NT8; nt++) dsacc[nt][0] = dsacc[nt][1] = dsacc[nt][2] = dsacc[nt][3] = 0.f;
 
   const float c = scale * LOG2E;
-  const int r0 = warp * 16;                       // this warp's query tile (phase A) / key tile (phase B)
+  const int role = warp >> 2;                      // 0: phase A (queries), 1: phase B (keys)
+  const int r0 = (warp & 3) * 16;                 // this warp's query tile (phase A) / key tile (phase B)
   const int rA = r0 + (lane >> 2), rB = rA + 8;
   const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;  // A-fragment rows of the tile
 
   for (; win < nwin_total; win += gridDim.y, stage ^= 1) {
     const int nxt = win + gridDim.y;
-    if (nxt < nwin_total && g.dbg != 1)
-      issue7<true>(g, nxt, h, qkv, qkv_bias, dout, out, lse, tiles + (stage ^ 1) * 5 * TILE7, Lrawb + (stage ^ 1) * 64,
+    if (nxt < nwin_total)
+      issue7<true, NTHREADS>(g, nxt, h, qkv, bchunk, dout, out, lse, tiles + (stage ^ 1) * 5 * TILE7, Lrawb + (stage ^ 1) * 64,
                    tokb + (stage ^ 1) * 64, ridb + (stage ^ 1) * 64);
     cp_async_commit();
     cp_async_wait<1>();
@@ -267,27 +288,24 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
     const int* tok = tokb + stage * 64;
     const int* rid = ridb + stage * 64;
     if (g.dbg == 2) { __syncthreads(); continue; }
-    {  // D[t] = rowsum(dO * O): two threads per row
-      const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
-      float part = 0.f;
+    {  // D[t] = rowsum(dO * O): four threads per row
+      const int t = threadIdx.x >> 2, qt = threadIdx.x & 3;
+      float fd[8], fo[8], part = 0.f;
+      unpack8(*reinterpret_cast<const bf16x8*>(dOs + t * LD + qt * 8), fd);
+      unpack8(*reinterpret_cast<const bf16x8*>(Os + t * LD + qt * 8), fo);
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
-        float fd[8], fo[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(dOs + t * LD + half * 16 + k * 8), fd);
-        unpack8(*reinterpret_cast<const bf16x8*>(Os + t * LD + half * 16 + k * 8), fo);
-#pragma unroll
-        for (int j = 0; j < 8; j++) part += fd[j] * fo[j];
-      }
+      for (int j = 0; j < 8; j++) part += fd[j] * fo[j];
       part += __shfl_xor_sync(0xffffffffu, part, 1);
-      if (half == 0) Dsm[t] = part;
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      if (qt == 0) Dsm[t] = part;
     }
     __syncthreads();
 
     const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
     int ridA = 0, ridB = 0;
     if (SHIFT) { ridA = rid[rA]; ridB = rid[rB]; }
-    // ---------------- phase A: rows = queries ----------------
-    {
+    // ---------------- phase A: rows = queries (warps 0-3) ----------------
+    if (role == 0) {
       uint32_t qa[2][4], da[2][4];
       ldsm_x4(qa[0], Qs + frag_off);
       ldsm_x4(qa[1], Qs + frag_off + 16);
@@ -356,8 +374,8 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
       }
       colsum_to_smem(dq, scale, dqb, lane);
     }
-    // ---------------- phase B: rows = keys (transposed recompute) ----------------
-    {
+    // ---------------- phase B: rows = keys, transposed recompute (warps 4-7) ----------------
+    else {
       uint32_t ka[2][4], va[2][4];
       ldsm_x4(ka[0], Ks + frag_off);
       ldsm_x4(ka[1], Ks + frag_off + 16);
@@ -452,14 +470,16 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
   cp_async_wait<0>();
   // flush the register-resident rel-pos-bias gradient of this warp's query rows.  dS was formed with the true
   // probabilities, so it is the gradient w.r.t. the natural-domain score, i.e. w.r.t. the table entry.
+  if (role == 0) {
 #pragma unroll
-  for (int nt = 0; nt < C::NT8; nt++)
+    for (int nt = 0; nt < C::NT8; nt++)
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int row = (e < 2) ? rA : rB;
-      const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
-      if (row < C::NT && col < C::NT) atomicAdd(&dbt[bias_index<WS>(row, col)], dsacc[nt][e]);
-    }
+      for (int e = 0; e < 4; e++) {
+        const int row = (e < 2) ? rA : rB;
+        const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
+        if (row < C::NT && col < C::NT) atomicAdd(&dbt[bias_index<WS>(row, col)], dsacc[nt][e]);
+      }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < C::NB; i += NTHREADS) atomicAdd(&dbias_table[i * g.nH + h], dbt[i]);
   for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS)

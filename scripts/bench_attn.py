@@ -36,7 +36,7 @@ for dbg in ("0", "1", "2"):
             tf, tb = e[0].elapsed_time(e[1]) / 5, e[1].elapsed_time(e[2]) / 5
             tot_f += tf
             tot_b += tb
-            if dbg == "0":
-                print(f"B={B} H={H} C={C} nH={nH} shift={shift}: fwd {tf*1e3:.0f} us  bwd {tb*1e3:.0f} us  "
+            if True:
+                print(f"dbg={dbg} " +f"B={B} H={H} C={C} nH={nH} shift={shift}: fwd {tf*1e3:.0f} us  bwd {tb*1e3:.0f} us  "
                       f"fwd {B*H*H*C*8/tf/1e6:.0f} GB/s  bwd {B*H*H*C*16/tb/1e6:.0f} GB/s")
     print(f"ESVIT_ATTN_DBG={dbg}: sum fwd {tot_f:.3f} ms  sum bwd {tot_b:.3f} ms")
