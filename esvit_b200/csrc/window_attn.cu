@@ -452,14 +452,14 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
     cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<true>, smem);
     if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<false>, smem);
     if (e != cudaSuccess) return (int)e;
-    int gx = (esvit_num_sms() * 8 + nH - 1) / nH;  // 2 CTAs (of 8 warps) / SM resident, ~4 waves of persistent CTAs
+    int gx = (esvit_num_sms() * 12 + nH - 1) / nH;  // 3 CTAs / SM resident, ~4 waves of persistent CTAs
     if (gx > nwin) gx = nwin;
     if (shift > 0)
-      wa::window_attn_bwd7_kernel<true><<<dim3(nH, gx), 256, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
+      wa::window_attn_bwd7_kernel<true><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                          (const bf16*)dout, lse, (bf16*)dqkv,
                                                                          dbias_table, dqkv_bias, g, scale, nwin);
     else
-      wa::window_attn_bwd7_kernel<false><<<dim3(nH, gx), 256, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
+      wa::window_attn_bwd7_kernel<false><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                           (const bf16*)dout, lse, (bf16*)dqkv,
                                                                           dbias_table, dqkv_bias, g, scale, nwin);
   } else {

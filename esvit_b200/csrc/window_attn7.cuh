@@ -221,17 +221,16 @@ static size_t fwd7_smem() { return (size_t)2 * 3 * TILE7 * 2 + (size_t)4 * 64 * 
 //                                   -> dV = P^T dO, dK = dS^T Q straight from the accumulator fragments
 // qkv-bias gradients are the column sums of dQ / dK / dV over all 49 slots (padded ones included).
 template <bool SHIFT>
-__global__ void __launch_bounds__(256, 2) window_attn_bwd7_kernel(
+__global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
     const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
     int nwin_total) {
   constexpr int WS = 7;
   using C = Cfg<WS>;
-  // 8 warps: warps 0-3 run phase A (one 16-query tile each), warps 4-7 run phase B (one 16-key tile each) of the SAME
-  // (window, head) concurrently - both phases only read the shared tiles, so the unit's latency is halved and the
-  // SM holds twice the warps for the same shared memory.
-  constexpr int NTHREADS = 256;
+  // (a variant that ran phase A and phase B on two concurrent 4-warp groups of an 8-warp CTA measured 20 % SLOWER:
+  // 2 CTAs/SM at the 128-register cap lose more than the halved per-window latency gains)
+  constexpr int NTHREADS = 128;
   static_assert(C::KP == 64 && C::NW == 4, "fast path assumes a 64-slot window and 4 tiles per phase");
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* tiles = reinterpret_cast<bf16*>(smraw);                       // [2 stages][Q | K | V | dO | O]
@@ -266,8 +265,7 @@ __global__ void __launch_bounds__(256, 2) window_attn_bwd7_kernel(
   for (int nt = 0; nt < C::NT8; nt++) dsacc[nt][0] = dsacc[nt][1] = dsacc[nt][2] = dsacc[nt][3] = 0.f;
 
   const float c = scale * LOG2E;
-  const int role = warp >> 2;                      // 0: phase A (queries), 1: phase B (keys)
-  const int r0 = (warp & 3) * 16;                 // this warp's query tile (phase A) / key tile (phase B)
+  const int r0 = warp * 16;                       // this warp's query tile (phase A) / key tile (phase B)
   const int rA = r0 + (lane >> 2), rB = rA + 8;
   const int frag_off = (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;  // A-fragment rows of the tile
 
@@ -288,24 +286,27 @@ __global__ void __launch_bounds__(256, 2) window_attn_bwd7_kernel(
     const int* tok = tokb + stage * 64;
     const int* rid = ridb + stage * 64;
     if (g.dbg == 2) { __syncthreads(); continue; }
-    {  // D[t] = rowsum(dO * O): four threads per row
-      const int t = threadIdx.x >> 2, qt = threadIdx.x & 3;
-      float fd[8], fo[8], part = 0.f;
-      unpack8(*reinterpret_cast<const bf16x8*>(dOs + t * LD + qt * 8), fd);
-      unpack8(*reinterpret_cast<const bf16x8*>(Os + t * LD + qt * 8), fo);
+    {  // D[t] = rowsum(dO * O): two threads per row
+      const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
+      float part = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; j++) part += fd[j] * fo[j];
+      for (int k = 0; k < 2; k++) {
+        float fd[8], fo[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dOs + t * LD + half * 16 + k * 8), fd);
+        unpack8(*reinterpret_cast<const bf16x8*>(Os + t * LD + half * 16 + k * 8), fo);
+#pragma unroll
+        for (int j = 0; j < 8; j++) part += fd[j] * fo[j];
+      }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      if (qt == 0) Dsm[t] = part;
+      if (half == 0) Dsm[t] = part;
     }
     __syncthreads();
 
     const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
     int ridA = 0, ridB = 0;
     if (SHIFT) { ridA = rid[rA]; ridB = rid[rB]; }
-    // ---------------- phase A: rows = queries (warps 0-3) ----------------
-    if (role == 0) {
+    // ---------------- phase A: rows = queries ----------------
+    {
       uint32_t qa[2][4], da[2][4];
       ldsm_x4(qa[0], Qs + frag_off);
       ldsm_x4(qa[1], Qs + frag_off + 16);
@@ -374,8 +375,8 @@ __global__ void __launch_bounds__(256, 2) window_attn_bwd7_kernel(
       }
       colsum_to_smem(dq, scale, dqb, lane);
     }
-    // ---------------- phase B: rows = keys, transposed recompute (warps 4-7) ----------------
-    else {
+    // ---------------- phase B: rows = keys (transposed recompute) ----------------
+    {
       uint32_t ka[2][4], va[2][4];
       ldsm_x4(ka[0], Ks + frag_off);
       ldsm_x4(ka[1], Ks + frag_off + 16);
@@ -470,16 +471,14 @@ __global__ void __launch_bounds__(256, 2) window_attn_bwd7_kernel(
   cp_async_wait<0>();
   // flush the register-resident rel-pos-bias gradient of this warp's query rows.  dS was formed with the true
   // probabilities, so it is the gradient w.r.t. the natural-domain score, i.e. w.r.t. the table entry.
-  if (role == 0) {
 #pragma unroll
-    for (int nt = 0; nt < C::NT8; nt++)
+  for (int nt = 0; nt < C::NT8; nt++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int row = (e < 2) ? rA : rB;
-        const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
-        if (row < C::NT && col < C::NT) atomicAdd(&dbt[bias_index<WS>(row, col)], dsacc[nt][e]);
-      }
-  }
+    for (int e = 0; e < 4; e++) {
+      const int row = (e < 2) ? rA : rB;
+      const int col = nt * 8 + (lane & 3) * 2 + (e & 1);
+      if (row < C::NT && col < C::NT) atomicAdd(&dbt[bias_index<WS>(row, col)], dsacc[nt][e]);
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < C::NB; i += NTHREADS) atomicAdd(&dbias_table[i * g.nH + h], dbt[i]);
   for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS)
