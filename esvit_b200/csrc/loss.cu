@@ -80,9 +80,11 @@ __global__ void __launch_bounds__(LT) row_lse_kernel(const bf16* __restrict__ x,
 }
 
 // row_loss[r] = n_r * lse_s[r] - sum_j sum_k exp(t~[tj,k] - lse_t[tj]) * s[r,k] * inv_tau_s
+// The student log-sum-exp is accumulated (online max/sum) in the SAME pass over the row - the dot term does not depend
+// on it - and written to lse_s for the backward: the student logits are read once, not twice.
 __global__ void __launch_bounds__(LT) dino_ce_fwd_kernel(
     const bf16* __restrict__ s, const bf16* __restrict__ t, const float* __restrict__ center,
-    const float* __restrict__ lse_s, const float* __restrict__ lse_t, const int* __restrict__ trow,
+    float* __restrict__ lse_s, const float* __restrict__ lse_t, const int* __restrict__ trow,
     float inv_temp_t, float inv_tau_s, float* __restrict__ row_loss, int K) {
   const long long r = blockIdx.x;
   const int t0 = trow[2 * r], t1 = trow[2 * r + 1];
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(LT) dino_ce_fwd_kernel(
   const bf16x8* tr0 = t0 >= 0 ? reinterpret_cast<const bf16x8*>(t + (long long)t0 * K) : nullptr;
   const bf16x8* tr1 = t1 >= 0 ? reinterpret_cast<const bf16x8*>(t + (long long)t1 * K) : nullptr;
   const float l0 = t0 >= 0 ? lse_t[t0] : 0.f, l1 = t1 >= 0 ? lse_t[t1] : 0.f;
-  float acc = 0.f;
+  float acc = 0.f, m = -INFINITY, sm = 0.f;
   for (int i = threadIdx.x; i < K / 8; i += LT) {
     float fs[8];
     unpack8(sr[i], fs);
@@ -112,13 +114,25 @@ __global__ void __launch_bounds__(LT) dino_ce_fwd_kernel(
 #pragma unroll
       for (int j = 0; j < 8; j++) q[j] += __expf((ft[j] - c[j]) * inv_temp_t - l1);
     }
+    float lm = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc += q[j] * fs[j];
+    for (int j = 0; j < 8; j++) {
+      acc += q[j] * fs[j];
+      fs[j] *= inv_tau_s;
+      lm = fmaxf(lm, fs[j]);
+    }
+    if (lm > m) { sm *= __expf(m - lm); m = lm; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) sm += __expf(fs[j] - m);
   }
-  acc = block_sum(acc);
+  block_reduce_ms(m, sm);
+  __shared__ float lse_sh;
+  if (threadIdx.x == 0) lse_sh = m + logf(sm);
+  acc = block_sum(acc);  // (contains the __syncthreads that publishes lse_sh)
   if (threadIdx.x == 0) {
     const float n = (float)((t0 >= 0) + (t1 >= 0));
-    row_loss[r] = n * lse_s[r] - acc * inv_tau_s;
+    lse_s[r] = lse_sh;
+    row_loss[r] = n * lse_sh - acc * inv_tau_s;
   }
 }
 
@@ -306,7 +320,7 @@ ESVIT_API int esvit_row_lse(const void* x, const float* center, float inv_temp, 
   ESVIT_LAUNCH_CHECK();
 }
 
-ESVIT_API int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, const float* lse_s,
+ESVIT_API int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, float* lse_s,
                                 const float* lse_t, const int* trow, float inv_temp_t, float inv_tau_s,
                                 float* row_loss, long long R, int K, void* stream) {
   if (K % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;

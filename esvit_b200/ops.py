@@ -459,8 +459,7 @@ class DinoCEFn(Function):
         center, lse_t, w = _chk(center, F32, "center"), _chk(lse_t, F32, "lse_t"), _chk(w, F32, "w")
         trow = _chk(trow, torch.int32, "trow")
         R, K = s.shape
-        lse_s = torch.empty(R, dtype=F32, device=s.device)
-        _lib.call("esvit_row_lse", _p(s), None, inv_tau_s, _p(lse_s), R, K, _stream())
+        lse_s = torch.empty(R, dtype=F32, device=s.device)  # written by the CE kernel itself (one pass over s)
         row_loss = torch.empty(R, dtype=F32, device=s.device)
         _lib.call("esvit_dino_ce_fwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), inv_temp_t, inv_tau_s,
                   _p(row_loss), R, K, _stream())

@@ -97,11 +97,12 @@ int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, con
 
 /* ---- DINOLoss / DDINOLoss ---------------------------------------------------- main_esvit.py:620-648, :683-750
  * row_lse: lse[r] = log sum_k exp((x[r,k] - center[k]) * inv_temp)   (center NULL for student rows).
- * dino_ce_fwd: row_loss[r] = n_r*lse_s[r] - sum_j <softmax((t[trow[r][j]]-center)*inv_temp_t), s[r]*inv_tau_s>
+ * dino_ce_fwd: row_loss[r] = n_r*lse_s[r] - sum_j <softmax((t[trow[r][j]]-center)*inv_temp_t), s[r]*inv_tau_s>;
+ *   lse_s[r] = LSE(s[r]*inv_tau_s) is an OUTPUT (computed in the same pass, kept for the backward)
  * dino_ce_bwd: ds[r] = gscale[0]*w[r]*inv_tau_s * (n_r*softmax(s[r]*inv_tau_s) - sum_j q_j)   (bf16 out)
  * trow int32 [R,2], -1 = no pair.  s/t bf16 [R,K]/[Rt,K], K % 8 == 0. */
 int esvit_row_lse(const void* x, const float* center, float inv_temp, float* lse, long long R, int K, void* stream);
-int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, const float* lse_s, const float* lse_t,
+int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, float* lse_s, const float* lse_t,
                       const int* trow, float inv_temp_t, float inv_tau_s, float* row_loss, long long R, int K,
                       void* stream);
 int esvit_dino_ce_bwd(const void* s, const void* t, const float* center, const float* lse_s, const float* lse_t,

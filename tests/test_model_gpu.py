@@ -143,3 +143,52 @@ def test_cuda_graph_step_equals_eager_step():
     for (n, a), b in zip(sE.named_parameters(), sG.parameters()):
         assert_close(b, a, 2e-3, n)
     assert_close(lG.center, lE.center, 1e-3, "center")
+
+
+def test_window14_model_matches_oracle():
+    """Swin with WINDOW_SIZE 14 (the Swin-S/B W14 configs of BASELINE.json): multi-crop forward, DDINO loss and
+    gradients of the CUDA path against the CPU oracle on the same random-init weights and seeded crops.  Covers the
+    N=196 attention kernels inside a model: 2x2 windows with shift 7, windows clamped to the nominal resolution, local
+    crops padded 12 -> 14 (single window that still gets a shift mask) and 6 -> 14."""
+    from esvit_b200 import engine
+    from oracle import losses as L
+    from oracle import step as ST
+    from oracle import swin as S
+    spec = dict(embed_dim=32, depths=[2, 2, 2], num_heads=[1, 2, 4], window_size=14, drop_path_rate=0.0)
+    K, ncrops, B = 256, 4, 2
+    step, student, teacher, loss = engine.make_step(out_dim=K, ncrops=ncrops, dense=True, device="cuda:0", img_size=112,
+                                                    head_kwargs=dict(hidden_dim=64, bottleneck_dim=32), spec=spec, seed=3)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():  # non-trivial biases / LN affine / bias tables
+        for n, p in student.named_parameters():
+            if n.endswith(".bias") or (p.dim() == 1 and "norm" in n) or "relative_position_bias_table" in n:
+                p.add_(torch.randn(p.shape, generator=g).to(p.device) * 0.1)
+    teacher.load_state_dict(student.state_dict())
+    crops = ST.synthetic_crops(B, ncrops - 2, seed=5, global_size=112, local_size=48)
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith("weight_g"))
+          for k, v in student.state_dict().items()}
+    ospec = S.SwinSpec(img_size=112, embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), window_size=14,
+                       use_dense_prediction=True)
+    with torch.no_grad():
+        t_ref = S.multicrop_forward(crops[:2], {k: v.detach() for k, v in sd.items()}, ospec)
+    s_ref = S.multicrop_forward(crops, sd, ospec)
+    l_ref = L.ddino_loss(s_ref, t_ref, torch.zeros(1, K), torch.zeros(1, K), ncrops, 0.04)
+    l_ref.backward()
+    cc = [c.cuda() for c in crops]
+    with torch.no_grad():
+        t = teacher(cc[:2])
+    s = student(cc)
+    l = loss(s, t, 0, None)
+    l.backward()
+    assert s[3] == s_ref[3]
+    for a, b, name in zip(s[:3], s_ref[:3], ("cls", "region", "fea")):
+        assert_close(a, b, TOL_BF16_ACT, "w14 " + name)
+    assert abs(float(l) - float(l_ref)) < 5e-3 * abs(float(l_ref)), (float(l), float(l_ref))
+    bad = {}
+    for n, p in student.named_parameters():
+        if sd[n].grad is None:
+            continue
+        r = rel(p.grad, sd[n].grad)
+        if r >= TOL_BF16_GRAD and float(sd[n].grad.norm()) > 1e-7:
+            bad[n] = r
+    assert not bad, bad
