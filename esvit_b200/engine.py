@@ -17,7 +17,7 @@ import torch.nn as nn
 
 import torch.distributed as dist
 
-from . import utils
+from . import ops, utils
 from .losses import DDINOLoss, DINOLoss
 from .optim import FusedAdamWEMA
 from .swin_transformer import SwinTransformer
@@ -84,6 +84,7 @@ class SelfDistillStep:
             self.opt.zero_grad()
         else:
             self.opt.zero_grad(set_to_none=True)
+        ops.begin_step(loss.device)  # one zero-filled arena for all small gradient accumulators of this backward
         loss.backward()
         if self.grad_allreduce and dist.is_initialized() and dist.get_world_size() > 1:
             grads = [p.grad for p in self.student.parameters() if p.grad is not None]

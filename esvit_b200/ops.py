@@ -28,6 +28,34 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Arena:
+    """One zero-filled fp32 buffer per training step from which the backward kernels' small ACCUMULATED outputs
+    (dgamma / dbeta / bias gradients / rel-pos-table gradients) are carved: one memset per step instead of ~340 tiny
+    fill kernels.  Regions are never handed out twice, so a stale arena is still correct (just smaller)."""
+    buf: Optional[Tensor] = None
+    off = 0
+
+
+def begin_step(device, nfloats: int = 1 << 22) -> None:
+    """Call once per step before backward (engine.SelfDistillStep does); optional - without it ops fall back to
+    torch.zeros per accumulator."""
+    _Arena.buf = torch.zeros(nfloats, dtype=F32, device=device)
+    _Arena.off = 0
+
+
+def _zeros(shape, device) -> Tensor:
+    n = 1
+    for d in shape:
+        n *= int(d)
+    buf = _Arena.buf
+    n16 = (n + 3) & ~3  # keep every region 16-byte aligned (vectorised optimiser reads)
+    if buf is not None and buf.device == torch.device(device) and _Arena.off + n16 <= buf.numel():
+        v = buf[_Arena.off:_Arena.off + n].view(*shape)
+        _Arena.off += n16
+        return v
+    return torch.zeros(*shape, dtype=F32, device=device)
+
+
 def _chk(t: Optional[Tensor], dtype, name: str) -> Optional[Tensor]:
     if t is None:
         return None
@@ -84,7 +112,7 @@ class AddLayerNormFn(Function):
             g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
         dx = torch.empty_like(xout)
         ddelta = torch.empty(xout.shape, dtype=BF16, device=xout.device)
-        acc = torch.zeros(3, C, dtype=F32, device=xout.device)  # dgamma | dbeta | ddelta_bias
+        acc = _zeros((3, C), xout.device)  # dgamma | dbeta | ddelta_bias
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, _p(g_xout), _p(xout), _p(mean), _p(rstd),
                   _p(gamma), _p(keep), ctx.tps, _p(dx), _p(ddelta), _p(acc[0]), _p(acc[1]),
                   _p(acc[2]) if ctx.has_dbias else None, T, C, _stream())
@@ -110,7 +138,7 @@ class LayerNormFn(Function):
         T, C = x.numel() // x.shape[-1], x.shape[-1]
         g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
         dx = torch.empty_like(x)
-        acc = torch.zeros(2, C, dtype=F32, device=x.device)
+        acc = _zeros((2, C), x.device)
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, None, _p(x), _p(mean), _p(rstd), _p(gamma),
                   None, 1, _p(dx), None, _p(acc[0]), _p(acc[1]), None, T, C, _stream())
         return dx, acc[0], acc[1], None, None
@@ -136,7 +164,7 @@ class ResidualAddFn(Function):
         g = _chk(g, F32, "g")
         T, C = g.numel() // g.shape[-1], g.shape[-1]
         ddelta = torch.empty(g.shape, dtype=BF16, device=g.device)
-        db = torch.zeros(C, dtype=F32, device=g.device) if ctx.has_dbias else None
+        db = _zeros((C,), g.device) if ctx.has_dbias else None
         _lib.call("esvit_add_ln_bwd", None, 0, _p(g), None, None, None, None, _p(keep), ctx.tps, None, _p(ddelta),
                   None, None, _p(db), T, C, _stream())
         return g, ddelta, db, None
@@ -181,7 +209,8 @@ class PatchMergeLNFn(Function):
         B, L, C = x.shape
         g = _chk(g, BF16, "g")
         dx = torch.empty_like(x)
-        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        acc = _zeros((2, gamma.numel()), x.device)
+        dgamma, dbeta = acc[0], acc[1]
         _lib.call("esvit_patch_merge_ln_bwd", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma),
                   _p(dbeta), B, H, W, C, _stream())
         return dx, dgamma, dbeta, None, None, None
@@ -236,8 +265,9 @@ class PatchEmbedFn(Function):
         B, _, H, W = img.shape
         E = w.shape[0]
         g = _chk(g, F32, "g")
-        dw, db = torch.zeros_like(w), torch.zeros_like(bias)
-        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        dw = _zeros(tuple(w.shape), w.device)
+        acc = _zeros((3, E), w.device)
+        db, dgamma, dbeta = acc[0], acc[1], acc[2]
         _lib.call("esvit_patch_embed_bwd", _p(img), _p(w), _p(bias), _p(gamma), _p(mean), _p(rstd), _p(g), _p(dw),
                   _p(db), _p(dgamma), _p(dbeta), B, H, W, E, _stream())
         return None, dw, db, dgamma, dbeta, None
@@ -275,8 +305,8 @@ class WindowAttentionFn(Function):
         B, H, W, C, nH, ws, shift, scale = ctx.geo
         g = _chk(g, BF16, "g")
         dqkv = torch.empty_like(qkv)
-        dtable = torch.zeros_like(bias_table)
-        dqb = torch.zeros(3 * C, dtype=F32, device=qkv.device)
+        dtable = _zeros(tuple(bias_table.shape), qkv.device)
+        dqb = _zeros((3 * C,), qkv.device)
         bws = torch.empty(nH * 4096, dtype=F32, device=qkv.device)
         _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(g), _p(lse), _p(dqkv),
                   _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
@@ -322,7 +352,7 @@ class BiasGeluFn(Function):
         g = _chk(g, BF16, "g")
         N = x.shape[-1]
         dx = torch.empty_like(x)
-        db = torch.zeros(ctx.bias_meta[0], dtype=F32, device=ctx.bias_meta[1])
+        db = _zeros(tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
         _lib.call("esvit_gelu_bwd_dbias", _p(x), _p(g), _p(dx), _p(db), x.numel() // N, N, _stream())
         return dx, db
 
@@ -360,7 +390,7 @@ class LinearGeluFn(Function):
         g = _chk(g, BF16, "g")
         N = pre.shape[-1]
         dh = torch.empty_like(pre)
-        db = torch.zeros(ctx.bias_meta[0], dtype=F32, device=ctx.bias_meta[1])
+        db = _zeros(tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
         _lib.call("esvit_mul_bwd_dbias", _p(pre), _p(g), _p(dh), _p(db), pre.numel() // N, N, _stream())
         dh2 = dh.reshape(-1, N)
         dx = (dh2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
