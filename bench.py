@@ -31,6 +31,15 @@ METRIC = "multi-crop images/sec, Swin-T W7 pretrain step (2 global 224^2 + 8 loc
 WORKLOAD = "swin_tiny_w7 2+8 crops DDINOLoss out_dim=65536 (BASELINE.json configs[1])"
 
 
+def describe(args):
+    """metric / workload strings; the defaults are BASELINE.json configs[1], other --arch values are parity-test configs."""
+    if args.arch == "swin_tiny_w7" and args.local_crops == 8 and args.out_dim == 65536:
+        return METRIC, WORKLOAD
+    return (f"multi-crop images/sec, {args.arch} pretrain step (2 global 224^2 + {args.local_crops} local 96^2 crops, "
+            f"DDINOLoss V+R, K={args.out_dim})",
+            f"{args.arch} 2+{args.local_crops} crops DDINOLoss out_dim={args.out_dim} (not the headline config)")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,7 +227,9 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------------
 def main():
+    global METRIC, WORKLOAD
     args = parse()
+    METRIC, WORKLOAD = describe(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -364,6 +375,9 @@ def main():
         # tcgen05 fc1 GEMM + bias + GELU: reads A (M*K) and W, writes out and gelu' (2*M*N) in bf16
         r_gemm = agg("esvit_gemm_bias_act", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
                      "tg::gemm_bias_act_kernel tcgen05 fc1+bias+GELU (all launches of a step)")
+        if r_bwd:  # dram__bytes_read+write of one launch from `ncu --set full` (profiles/r01_v7_ncu_full_key_metrics.txt)
+            r_bwd["traffic"] = {"ncu_launch": "window_attn_bwd7_kernel<1> grid (6,296): stage-1 global crops, 100352 tokens x C=192",
+                                "dram_bytes": 279.3e6, "algorithmic_bytes": 16 * 100352 * 192}
         cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm) if r]
         if cands:
             cands.sort(key=lambda r: -r["ms_per_step"])
