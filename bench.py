@@ -208,7 +208,7 @@ def run_reference(args):
     device = args.device or "cpu"
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     if device == "cpu":
-        steps, warmup = min(steps, 5), min(warmup, 1)  # bounded sample: ~1.5 s per B=2 step on 8 cores
+        steps, warmup = min(steps, 3), min(warmup, 1)  # bounded sample: ~1-8 s per B=2 step depending on the host
         batch = args.ref_batch
     else:
         batch = args.batch
