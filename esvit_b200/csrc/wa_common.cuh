@@ -60,8 +60,10 @@ struct Cfg {
 // gather the q/k/v rows of one (window, head) into smem.  qkv already contains the qkv bias (GEMM epilogue); a padded
 // slot holds the bf16 bias alone because the reference zero-pads the normalised activations (:287-290).
 // All global loads are issued before any is consumed (one exposed DRAM latency, not PER of them).
+// qbs: this head's bf16 bias [3][32] staged in SHARED memory by the caller (padded slots must not all hit the same
+// global cache lines - with local crops thousands of CTAs would serialise on them).
 template <int WS, int NTHREADS>
-__device__ __forceinline__ void load_qkv(const Geo& g, const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias,
+__device__ __forceinline__ void load_qkv(const Geo& g, const bf16* __restrict__ qkv, const bf16* qbs,
                                          int h, const int* tok, bf16* Qs, bf16* Ks, bf16* Vs) {
   using C = Cfg<WS>;
   constexpr int TOTAL = C::KP * 12;                       // 16-byte chunks: KP rows x (q,k,v) x 4
@@ -75,9 +77,10 @@ __device__ __forceinline__ void load_qkv(const Geo& g, const bf16* __restrict__ 
       const int t = id / 12, rem = id - t * 12, part = rem >> 2, c16 = rem & 3;
       if (t < C::NT) {
         const int tk = tok[t];
-        const bf16* src = tk >= 0 ? qkv + (long long)tk * 3 * g.C + part * g.C + h * HD + c16 * 8
-                                  : qkv_bias + part * g.C + h * HD + c16 * 8;
-        raw[k] = __ldg(reinterpret_cast<const uint4*>(src));
+        if (tk >= 0)
+          raw[k] = __ldg(reinterpret_cast<const uint4*>(qkv + (long long)tk * 3 * g.C + part * g.C + h * HD + c16 * 8));
+        else
+          raw[k] = *reinterpret_cast<const uint4*>(qbs + part * HD + c16 * 8);
       }
     }
   }

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_fwd_kernel(
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* Ks = Qs + C::KP * LD;
   bf16* Vs = Ks + C::KP * LD;
-  float* bt = reinterpret_cast<float*>(Vs + C::KP * LD);
+  bf16* qbs = Vs + C::KP * LD;  // [3][32] bf16 bias of this head (16-byte aligned: directly behind the tiles)
+  float* bt = reinterpret_cast<float*>(qbs + 3 * HD);
   int* tok = reinterpret_cast<int*>(bt + C::NB);
   int* rid = tok + C::KP;
 
@@ -50,8 +51,9 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_fwd_kernel(
     rid[i] = r;
   }
   for (int i = threadIdx.x; i < C::NB; i += NTHREADS) bt[i] = bias_table[i * g.nH + h];
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
   __syncthreads();
-  load_qkv<WS, NTHREADS>(g, qkv, qkv_bias, h, tok, Qs, Ks, Vs);
+  load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
   __syncthreads();
 
   for (int mt = warp; mt < C::MT; mt += C::NW) {
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
   bf16* dOs = Vs + C::KP * LD;
   bf16* Ps = dOs + C::KP * LD;       // [KP][PLD]  P chunk   (queries x chunk keys)
   bf16* dSs = Ps + C::KP * PLD;      // [KP][PLD]  dS chunk
-  float* bt = reinterpret_cast<float*>(dSs + C::KP * PLD);
+  bf16* qbs = dSs + C::KP * PLD;     // [3][32] bf16 bias of this head (16-byte aligned: directly behind the tiles)
+  float* bt = reinterpret_cast<float*>(qbs + 3 * HD);
   float* dbt = bt + C::NB;           // rel-pos bias grad bins (this head)
   float* dqb = dbt + C::NB;          // [3][32] qkv-bias grads of this head (column sums of dq / dk / dv)
   float* Dsm = dqb + 3 * HD;         // [KP] rowsum(dO * O)
@@ -183,7 +186,10 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
     bt[i] = bias_table[i * g.nH + h];
     dbt[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) dqb[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * HD; i += NTHREADS) {
+    dqb[i] = 0.f;
+    qbs[i] = qkv_bias[(i / HD) * g.C + h * HD + (i % HD)];
+  }
 
   for (int win = blockIdx.x; win < nwin_total; win += gridDim.x) {
     const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, b = win / (g.nWx * g.nWy);
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
       Lsm[i] = i < C::NT ? lse[((long long)win * g.nH + h) * C::NT + i] : 0.f;
     }
     __syncthreads();
-    load_qkv<WS, NTHREADS>(g, qkv, qkv_bias, h, tok, Qs, Ks, Vs);
+    load_qkv<WS, NTHREADS>(g, qkv, qbs, h, tok, Qs, Ks, Vs);
     load_do<WS, NTHREADS>(g, dout, out, h, tok, dOs, Dsm);
     __syncthreads();
 
@@ -371,13 +377,13 @@ __global__ void __launch_bounds__(Cfg<WS>::NW * 32) window_attn_bwd_kernel(
 template <int WS>
 size_t fwd_smem() {
   using C = Cfg<WS>;
-  return (size_t)3 * C::KP * LD * 2 + (size_t)C::NB * 4 + (size_t)2 * C::KP * 4;
+  return (size_t)3 * C::KP * LD * 2 + (size_t)((C::NB + 3) & ~3) * 4 + (size_t)2 * C::KP * 4 + 3 * HD * 2 + 64;
 }
 template <int WS>
 size_t bwd_smem() {
   using C = Cfg<WS>;
   return (size_t)4 * C::KP * LD * 2 + (size_t)2 * C::KP * PLD * 2 + (size_t)(2 * C::NB + 3 * HD + 2 * C::KP) * 4 +
-         (size_t)2 * C::KP * 4;
+         (size_t)2 * C::KP * 4 + 3 * HD * 2 + 64;
 }
 
 static bool make_geo(Geo& g, int B, int H, int W, int C, int nH, int ws, int shift) {
