@@ -366,8 +366,9 @@ def main():
         rows_t = B * 2 * Tg
         # attention backward (the largest of this repo's kernels by time): reads qkv (6C) + dO (2C) + O (2C), writes dqkv
         # (6C) bytes per token -> 16*C per token; forward: 8*C per token
-        r_bwd = agg("esvit_window_attn_bwd", lambda t: 16 * t["tokens"] * t["C"], "window_attn_bwd7_kernel (all launches of a step)")
-        r_fwd = agg("esvit_window_attn_fwd", lambda t: 8 * t["tokens"] * t["C"], "window_attn_fwd7_kernel (all launches of a step)")
+        wtag = "7_kernel" if "w14" not in args.arch else "14_kernel + 7_kernel (stage 3)"
+        r_bwd = agg("esvit_window_attn_bwd", lambda t: 16 * t["tokens"] * t["C"], f"window_attn_bwd{wtag} (all launches of a step)")
+        r_fwd = agg("esvit_window_attn_fwd", lambda t: 8 * t["tokens"] * t["C"], f"window_attn_fwd{wtag} (all launches of a step)")
         # region-row CE backward: read student rows + each paired teacher row once + write bf16 grads:
         # (170 + 98 + 170) rows x K x 2 B per image
         r_ce = agg("esvit_dino_ce_bwd", lambda t: (2 * rows_s + rows_t) * t["K"] * 2, "dino_ce_bwd_kernel (region rows)",
@@ -375,9 +376,10 @@ def main():
         # tcgen05 fc1 GEMM + bias + GELU: reads A (M*K) and W, writes out and gelu' (2*M*N) in bf16
         r_gemm = agg("esvit_gemm_bias_act", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
                      "tg::gemm_bias_act_kernel tcgen05 fc1+bias+GELU (all launches of a step)")
-        if r_bwd:  # dram__bytes_read+write of one launch from `ncu --set full` (profiles/r01_v7_ncu_full_key_metrics.txt)
+        if r_bwd and "w14" not in args.arch:
+            # dram__bytes_read+write of one launch from `ncu --set full` (profiles/r01_final_ncu_full_key_metrics.txt)
             r_bwd["traffic"] = {"ncu_launch": "window_attn_bwd7_kernel<1> grid (6,296): stage-1 global crops, 100352 tokens x C=192",
-                                "dram_bytes": 279.3e6, "algorithmic_bytes": 16 * 100352 * 192}
+                                "dram_bytes": 278.3e6, "algorithmic_bytes": 16 * 100352 * 192}
         cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm) if r]
         if cands:
             cands.sort(key=lambda r: -r["ms_per_step"])

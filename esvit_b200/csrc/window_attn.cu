@@ -21,6 +21,7 @@
 
 #include "wa_common.cuh"
 #include "window_attn7.cuh"
+#include "window_attn14.cuh"
 
 namespace wa {
 
@@ -398,6 +399,20 @@ static bool make_geo(Geo& g, int B, int H, int W, int C, int nH, int ws, int shi
   return true;
 }
 
+// persistent grid: `per_sm` resident CTAs per SM, heads on blockIdx.x.  ESVIT_ATTN_GY (tests) forces a small grid so a
+// few windows exercise the multi-window loops.
+static int windows_grid(int nwin, int nH, int per_sm) {
+  int gy = esvit_num_sms() * per_sm / nH;  // floor: one CTA too many would be a whole extra wave
+  if (gy < 1) gy = 1;
+  const char* e = getenv("ESVIT_ATTN_GY");
+  if (e && atoi(e) > 0) gy = atoi(e);
+  return gy > nwin ? nwin : gy;
+}
+static bool use_generic14() {
+  const char* e = getenv("ESVIT_ATTN_GENERIC14");  // A/B switch: the first (generic, ws-templated) kernels
+  return e && atoi(e) != 0;
+}
+
 template <typename K>
 static cudaError_t opt_in_smem(K kernel, size_t smem) {
   return smem > 48 * 1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -422,12 +437,21 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
     wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
     const size_t smem = wa::fwd7_smem();
-    int gx = (esvit_num_sms() * 16 + nH - 1) / nH;  // persistent: ~4 waves of 4 resident CTAs per SM
-    if (gx > nwin) gx = nwin;
+    const int gx = wa::windows_grid(nwin, nH, 16);  // persistent: ~4 waves of 4 resident CTAs per SM
     if (shift > 0)
       wa::window_attn_fwd7_kernel<true><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
     else
       wa::window_attn_fwd7_kernel<false><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
+  } else if (!wa::use_generic14()) {
+    const size_t smem = wa::fwd14_smem();
+    cudaError_t e = wa::opt_in_smem(wa::window_attn_fwd14_kernel<true>, smem);
+    if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_fwd14_kernel<false>, smem);
+    if (e != cudaSuccess) return (int)e;
+    const dim3 grid(nH, wa::windows_grid(nwin, nH, 2));
+    if (shift > 0)
+      wa::window_attn_fwd14_kernel<true><<<grid, wa::T14, smem, st>>>(q, qb, bias_table, (bf16*)out, lse, g, scale, nwin);
+    else
+      wa::window_attn_fwd14_kernel<false><<<grid, wa::T14, smem, st>>>(q, qb, bias_table, (bf16*)out, lse, g, scale, nwin);
   } else {
     const size_t smem = wa::fwd_smem<14>();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_fwd_kernel<14>, smem);
@@ -458,8 +482,7 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
     cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<true>, smem);
     if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<false>, smem);
     if (e != cudaSuccess) return (int)e;
-    int gx = (esvit_num_sms() * 12 + nH - 1) / nH;  // 3 CTAs / SM resident, ~4 waves of persistent CTAs
-    if (gx > nwin) gx = nwin;
+    const int gx = wa::windows_grid(nwin, nH, 12);  // 3 CTAs / SM resident, ~4 waves of persistent CTAs
     if (shift > 0)
       wa::window_attn_bwd7_kernel<true><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                          (const bf16*)dout, lse, (bf16*)dqkv,
@@ -468,6 +491,21 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
       wa::window_attn_bwd7_kernel<false><<<dim3(nH, gx), 128, smem, st>>>(q, qb, bias_ws, (const bf16*)out,
                                                                           (const bf16*)dout, lse, (bf16*)dqkv,
                                                                           dbias_table, dqkv_bias, g, scale, nwin);
+  } else if (!wa::use_generic14()) {
+    if (!bias_ws) return ESVIT_ERR_BAD_ARG;
+    const size_t smem = wa::bwd14_smem();
+    cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd14_kernel<true>, smem);
+    if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_bwd14_kernel<false>, smem);
+    if (e == cudaSuccess) e = cudaMemsetAsync(bias_ws, 0, (size_t)nH * wa::GACC14 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    const dim3 grid(nH, wa::windows_grid(nwin, nH, 2));
+    if (shift > 0)
+      wa::window_attn_bwd14_kernel<true><<<grid, wa::T14, smem, st>>>(q, qb, bias_table, (const bf16*)out, (const bf16*)dout,
+                                                                      lse, (bf16*)dqkv, bias_ws, dqkv_bias, g, scale, nwin);
+    else
+      wa::window_attn_bwd14_kernel<false><<<grid, wa::T14, smem, st>>>(q, qb, bias_table, (const bf16*)out, (const bf16*)dout,
+                                                                       lse, (bf16*)dqkv, bias_ws, dqkv_bias, g, scale, nwin);
+    wa::fold_dbias14_kernel<<<dim3(27, nH), 192, 0, st>>>(bias_ws, dbias_table, nH);
   } else {
     const size_t smem = wa::bwd_smem<14>();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd_kernel<14>, smem);

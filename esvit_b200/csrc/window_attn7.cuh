@@ -129,6 +129,18 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
     const int* tok = tokb + stage * 64;
     const int* rid = ridb + stage * 64;
     if (g.dbg == 2) { __syncthreads(); continue; }
+    const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
+    // a query tile whose 16 slots are all padding (local crops: the window rows below the map) produces only rows
+    // the reference crops away (:318-319) - skip its math; the warp's issue slots go to the co-resident CTAs
+    if (!__any_sync(0xffffffffu, tA >= 0 || tB >= 0)) {
+      if ((lane & 3) == 0) {  // keep the saved statistics defined (the backward skips the same tiles)
+        float* l = lse + ((long long)win * g.nH + h) * C::NT;
+        if (rA < C::NT) l[rA] = 0.f;
+        if (rB < C::NT) l[rB] = 0.f;
+      }
+      __syncthreads();
+      continue;
+    }
 
     uint32_t qa[2][4];
     ldsm_x4(qa[0], Qs + frag_off);
@@ -199,7 +211,6 @@ __global__ void __launch_bounds__(128, 4) window_attn_fwd7_kernel(
       mma16816(o[2], pa, vb[0], vb[1]);
       mma16816(o[3], pa, vb[2], vb[3]);
     }
-    const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
 #pragma unroll
     for (int dt = 0; dt < 4; dt++) {
       const int d = h * HD + dt * 8 + (lane & 3) * 2;
@@ -305,8 +316,13 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
     const int tA = rA < C::NT ? tok[rA] : -1, tB = rB < C::NT ? tok[rB] : -1;
     int ridA = 0, ridB = 0;
     if (SHIFT) { ridA = rid[rA]; ridB = rid[rB]; }
+    // 16-slot tiles that hold a real token (bit t = tile t).  An all-padding QUERY tile has dO = 0 (its rows are cropped
+    // away): dS = 0 there, so it adds nothing to dQ / dK / dV / the bias gradients and both phases skip it.  (Padded
+    // KEY tiles are kept: their dK / dV are part of the qkv-bias gradient.)
+    const unsigned b0 = __ballot_sync(0xffffffffu, tok[lane] >= 0), b1 = __ballot_sync(0xffffffffu, tok[lane + 32] >= 0);
+    const unsigned qvalid = ((b0 & 0xffffu) ? 1u : 0u) | ((b0 >> 16) ? 2u : 0u) | ((b1 & 0xffffu) ? 4u : 0u) | ((b1 >> 16) ? 8u : 0u);
     // ---------------- phase A: rows = queries ----------------
-    {
+    if ((qvalid >> warp) & 1u) {
       uint32_t qa[2][4], da[2][4];
       ldsm_x4(qa[0], Qs + frag_off);
       ldsm_x4(qa[1], Qs + frag_off + 16);
@@ -390,6 +406,7 @@ __global__ void __launch_bounds__(128, 3) window_attn_bwd7_kernel(
       }
 #pragma unroll
       for (int qq = 0; qq < 4; qq++) {
+        if (!((qvalid >> qq) & 1u)) continue;
         float pT[2][4], dsT[2][4];
 #pragma unroll
         for (int hf = 0; hf < 2; hf++) {

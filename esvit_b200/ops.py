@@ -274,6 +274,9 @@ class PatchEmbedFn(Function):
 
 
 # ------------------------------------------------------------------------------------------------------------
+ATTN_WS_FLOATS = 8192  # per head; include/esvit_b200.h (expanded bias for ws 7, bias-gradient accumulator for ws 14)
+
+
 class WindowAttentionFn(Function):
     """qkv bf16 [B, H*W, 3C] (qkv GEMM output incl. bias) -> attention output bf16 [B, H*W, C] in token order
     (pad / roll / partition / reverse folded in).  qkv_bias (fp32 [3C] parameter) supplies the value of padded slots
@@ -291,7 +294,7 @@ class WindowAttentionFn(Function):
         nwin = B * (-(-H // ws)) * (-(-W // ws))
         out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
         lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
-        bws = torch.empty(num_heads * 4096, dtype=F32, device=qkv.device)  # expanded rel-pos bias (kernel workspace)
+        bws = torch.empty(num_heads * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)  # kernel workspace
         _lib.call("esvit_window_attn_fwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(lse), B, H, W, C,
                   num_heads, ws, shift, scale, _stream())
         ctx.save_for_backward(qkv, qb, bias_table, out, lse)
@@ -307,7 +310,7 @@ class WindowAttentionFn(Function):
         dqkv = torch.empty_like(qkv)
         dtable = _zeros(tuple(bias_table.shape), qkv.device)
         dqb = _zeros((3 * C,), qkv.device)
-        bws = torch.empty(nH * 4096, dtype=F32, device=qkv.device)
+        bws = torch.empty(nH * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
         _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(g), _p(lse), _p(dqkv),
                   _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
         return dqkv, dqb, dtable, None, None, None, None, None, None

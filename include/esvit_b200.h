@@ -62,7 +62,8 @@ int esvit_patch_embed_bwd(const float* img, const float* w, const float* bias, c
  * qkv bf16 [B,H,W,3C] ([q|k|v][head][32]) is the qkv GEMM output including its bias; qkv_bias bf16 [3C] is what a
  * padded slot holds (the bias alone); bias_table fp32 [(2ws-1)^2, nH]; out bf16 [B,H,W,C]; lse fp32
  * [B*nWindows, nH, ws*ws].  ws in {7,14}; head_dim 32.
- * bias_ws fp32 [nH*4096]: caller-owned workspace, receives the rel-pos bias expanded to [nH][64][64] (ws = 7 path).
+ * bias_ws fp32 [nH*8192]: caller-owned scratch (ws 7: the rel-pos bias expanded to [nH][64][64]; ws 14 backward: the
+ * lane-expanded bias-gradient accumulator [nH][27][6][32], cleared and folded into dbias_table inside the call).
  * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] (complete qkv-bias gradient) ACCUMULATED. */
 int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws, void* out,
                           float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);

@@ -283,6 +283,19 @@ def test_swin_block_many_heads():
     _block_case(14, 7, 3, 384, 12, 14, seed=5)
 
 
+def test_swin_block_w14_many_heads():
+    _block_case(28, 14, 7, 256, 8, 28, seed=6)
+
+
+@pytest.mark.parametrize("gy", [1, 3])
+@pytest.mark.parametrize("H,ws,shift,res", [(28, 14, 7, 28), (24, 14, 0, 56), (28, 7, 3, 56), (24, 7, 3, 56)])
+def test_swin_block_persistent_loops(monkeypatch, gy, H, ws, shift, res):
+    """a forced small grid (ESVIT_ATTN_GY) makes every CTA walk several windows: pipeline stages wrap, per-CTA
+    accumulators (bias / qkv-bias gradients) span windows."""
+    monkeypatch.setenv("ESVIT_ATTN_GY", str(gy))
+    _block_case(H, ws, shift, 64, 2, res, seed=H + ws + shift + gy)
+
+
 def test_region_match_bit_exact_on_golden_features():
     """argmax indices bit-exact on identical feature inputs - features and expected indices are
     the reference's own (tests/golden)."""
