@@ -6,8 +6,6 @@ namespace wa {
 
 constexpr int HD = 32;  // head dim
 constexpr int LD = 40;  // smem row stride (bf16 elements) of the q/k/v/dO tiles: 80 B rows -> conflict-free ldmatrix
-constexpr int KC = 64;  // key chunk of the backward
-constexpr int PLD = KC + 8;  // smem row stride of the P / dS chunk tiles
 
 struct Geo {
   int B, H, W, C, nH, shift, Hp, Wp, nWx, nWy;
@@ -56,86 +54,6 @@ struct Cfg {
   static constexpr int NW = (WS == 7) ? 4 : 7;  // warps
   static constexpr int NB = (2 * WS - 1) * (2 * WS - 1);
 };
-
-// gather the q/k/v rows of one (window, head) into smem.  qkv already contains the qkv bias (GEMM epilogue); a padded
-// slot holds the bf16 bias alone because the reference zero-pads the normalised activations (:287-290).
-// All global loads are issued before any is consumed (one exposed DRAM latency, not PER of them).
-// qbs: this head's bf16 bias [3][32] staged in SHARED memory by the caller (padded slots must not all hit the same
-// global cache lines - with local crops thousands of CTAs would serialise on them).
-template <int WS, int NTHREADS>
-__device__ __forceinline__ void load_qkv(const Geo& g, const bf16* __restrict__ qkv, const bf16* qbs,
-                                         int h, const int* tok, bf16* Qs, bf16* Ks, bf16* Vs) {
-  using C = Cfg<WS>;
-  constexpr int TOTAL = C::KP * 12;                       // 16-byte chunks: KP rows x (q,k,v) x 4
-  constexpr int PER = (TOTAL + NTHREADS - 1) / NTHREADS;  // per thread
-  uint4 raw[PER];
-#pragma unroll
-  for (int k = 0; k < PER; k++) {
-    const int id = threadIdx.x + k * NTHREADS;
-    raw[k] = make_uint4(0, 0, 0, 0);
-    if (id < TOTAL) {
-      const int t = id / 12, rem = id - t * 12, part = rem >> 2, c16 = rem & 3;
-      if (t < C::NT) {
-        const int tk = tok[t];
-        if (tk >= 0)
-          raw[k] = __ldg(reinterpret_cast<const uint4*>(qkv + (long long)tk * 3 * g.C + part * g.C + h * HD + c16 * 8));
-        else
-          raw[k] = *reinterpret_cast<const uint4*>(qbs + part * HD + c16 * 8);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < PER; k++) {
-    const int id = threadIdx.x + k * NTHREADS;
-    if (id < TOTAL) {
-      const int t = id / 12, rem = id - t * 12, part = rem >> 2, c16 = rem & 3;
-      bf16* dst = (part == 0 ? Qs : (part == 1 ? Ks : Vs)) + t * LD + c16 * 8;
-      *reinterpret_cast<uint4*>(dst) = raw[k];
-    }
-  }
-}
-
-// dO rows of one (window, head) into smem (zero for padded slots: their outputs are cropped) and
-// D[t] = rowsum(dO * O); all loads issued up front.
-template <int WS, int NTHREADS>
-__device__ __forceinline__ void load_do(const Geo& g, const bf16* __restrict__ dout, const bf16* __restrict__ out,
-                                        int h, const int* tok, bf16* dOs, float* Dsm) {
-  using C = Cfg<WS>;
-  constexpr int TOTAL = C::KP * 4;
-  constexpr int PER = (TOTAL + NTHREADS - 1) / NTHREADS;
-  static_assert(TOTAL % 32 == 0, "whole warps enter/leave the loop together (shuffles below)");
-  uint4 dv[PER], ov[PER];
-#pragma unroll
-  for (int k = 0; k < PER; k++) {
-    const int id = threadIdx.x + k * NTHREADS;
-    dv[k] = make_uint4(0, 0, 0, 0);
-    ov[k] = make_uint4(0, 0, 0, 0);
-    if (id < TOTAL) {
-      const int t = id >> 2, c16 = id & 3;
-      const int tk = t < C::NT ? tok[t] : -1;
-      if (tk >= 0) {
-        dv[k] = __ldg(reinterpret_cast<const uint4*>(dout + (long long)tk * g.C + h * HD + c16 * 8));
-        ov[k] = __ldg(reinterpret_cast<const uint4*>(out + (long long)tk * g.C + h * HD + c16 * 8));
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < PER; k++) {
-    const int id = threadIdx.x + k * NTHREADS;
-    if (id < TOTAL) {
-      const int t = id >> 2, c16 = id & 3;
-      float fd[8], fo[8], part = 0.f;
-      unpack8(*reinterpret_cast<const bf16x8*>(&dv[k]), fd);
-      unpack8(*reinterpret_cast<const bf16x8*>(&ov[k]), fo);
-#pragma unroll
-      for (int j = 0; j < 8; j++) part += fd[j] * fo[j];
-      *reinterpret_cast<uint4*>(dOs + t * LD + c16 * 8) = dv[k];
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      if (c16 == 0) Dsm[t] = part;
-    }
-  }
-}
 
 // column sums of a 16 x 32 fp32 accumulator tile (4 d-tiles x C-fragment) added to dst[32] in shared memory
 __device__ __forceinline__ void colsum_to_smem(const float (&t)[4][4], float scale, float* dst, int lane) {

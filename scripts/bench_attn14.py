@@ -1,5 +1,5 @@
 """Micro-benchmark of the ws=14 window-attention kernels at the Swin-B W14 stage shapes (B=32: 64 global + 256 local
-images).  ESVIT_ATTN_GENERIC14=1 selects the first (generic) kernels for an A/B."""
+images).  (profiles/r01_v9_attn14_microbench.txt holds the A/B against the first, generic ws-templated kernels.)"""
 import os
 import sys
 
@@ -13,8 +13,7 @@ d = torch.device("cuda:0")
 shapes = [(64, 56, 128, 4, 0, 1), (64, 56, 128, 4, 7, 1), (64, 28, 256, 8, 0, 1), (64, 28, 256, 8, 7, 1),
           (64, 14, 512, 16, 0, 18), (256, 24, 128, 4, 0, 1), (256, 24, 128, 4, 7, 1), (256, 12, 256, 8, 0, 1),
           (256, 12, 256, 8, 7, 1), (256, 6, 512, 16, 0, 18)]
-for generic in ("0", "1"):
-    os.environ["ESVIT_ATTN_GENERIC14"] = generic
+for generic in ("0",):
     tot_f = tot_b = 0.0
     for (B, H, C, nH, shift, nblk) in shapes:
         qkv = torch.randn(B, H * H, 3 * C, device=d).to(torch.bfloat16).requires_grad_(True)
@@ -37,5 +36,5 @@ for generic in ("0", "1"):
         tf, tb = e[0].elapsed_time(e[1]) / 3, e[1].elapsed_time(e[2]) / 3
         tot_f += tf * nblk
         tot_b += tb * nblk
-        print(f"generic={generic} B={B} H={H} C={C} nH={nH} shift={shift}: fwd {tf*1e3:.0f} us  bwd {tb*1e3:.0f} us", flush=True)
-    print(f"ESVIT_ATTN_GENERIC14={generic}: weighted sum fwd {tot_f:.3f} ms  bwd {tot_b:.3f} ms (student pass, Swin-B W14, B=32)", flush=True)
+        print(f"B={B} H={H} C={C} nH={nH} shift={shift}: fwd {tf*1e3:.0f} us  bwd {tb*1e3:.0f} us", flush=True)
+    print(f"weighted sum fwd {tot_f:.3f} ms  bwd {tot_b:.3f} ms (student pass, Swin-B W14, B=32)", flush=True)
