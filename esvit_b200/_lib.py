@@ -30,6 +30,7 @@ SIGNATURES = {
     "esvit_window_attn_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     "esvit_window_attn_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     "esvit_gemm_bias_act": [P, P, P, P, P, L, I, I, I, P],
+    "esvit_gemm_mul_colsum": [P, P, P, P, P, P, L, I, I, P],
     "esvit_gelu_fwd": [P, P, L, P],
     "esvit_gelu_bwd": [P, P, P, L, P],
     "esvit_gelu_bwd_dbias": [P, P, P, P, L, I, P],
@@ -109,6 +110,7 @@ _META = {
     "esvit_window_attn_bwd": lambda a: {"tokens": int(a[-9]) * int(a[-8]) * int(a[-7]), "C": int(a[-6])},
     "esvit_window_attn_fwd": lambda a: {"tokens": int(a[-9]) * int(a[-8]) * int(a[-7]), "C": int(a[-6])},
     "esvit_gemm_bias_act": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7])},
+    "esvit_gemm_mul_colsum": lambda a: {"M": int(a[6]), "N": int(a[7]), "K": int(a[8])},
 }
 
 

@@ -20,7 +20,7 @@ namespace tg {
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_EPI_WARPS = 16, NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-17 epilogue
+constexpr int NUM_EPI_WARPS = 16, NUM_THREADS = 32 * (3 + NUM_EPI_WARPS);  // warp0 TMA, warp1 MMA, warps 2-17 epilogue, warp18 multiplier TMA
 constexpr int TMEM_COLS = 2 * BN;                                          // double-buffered accumulator
 constexpr int OUT_TILE_BYTES = BM * BN * 2;                                // bf16 staging tile of the TMA store
 constexpr int OUT_HALF_BYTES = BM * 64 * 2;                                // one 64-column (128-byte) swizzled box
@@ -132,10 +132,12 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
 
 struct Params {
   bf16* out;        // [M, N] act(A W^T + bias)
-  bf16* pre;        // [M, N] d act/dx at the pre-activation (gelu'(A W^T + bias)), written when act != 0 and pre != nullptr
+  bf16* pre;        // [M, N] d act/dx at the pre-activation (gelu'(A W^T + bias)), written when act == 1 and pre != nullptr
   const float* bias;  // [N] or nullptr
-  int M, N, K, act;   // act: 0 = identity, 1 = exact GELU
+  float* colsum;      // act == 2: [gridDim.x][N] per-CTA partial column sums of out (zeroed by the launcher)
+  int M, N, K, act;   // act: 0 = identity, 1 = exact GELU, 2 = out = (A W^T) * mult[M,N] (mult arrives through map_pre)
 };
+constexpr int ACT_MUL = 2;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                        const __grid_constant__ CUtensorMap map_b,
@@ -151,7 +153,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* mult_full = tmem_empty + 2;   // [2] act == 2: multiplier tile landed in the `pre` staging slot
+  uint64_t* mult_empty = mult_full + 2;   // [2] ... and has been consumed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mult_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN, k_blocks = (p.K + BK - 1) / BK;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS * 32); }
+    for (int i = 0; i < 2; i++) { mbar_init(&mult_full[i], 1); mbar_init(&mult_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 2) {  // one warp allocates TMEM (and frees it at the end)
@@ -190,6 +195,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
           tma_load_2d(sa + A_BYTES, &map_b, &full[stage], kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+    }
+  } else if (warp == 2 + NUM_EPI_WARPS) {
+    // ===================== multiplier stream (act == 2) =====================
+    // its own warp: waiting for a staging slot must not hold back the operand prefetch.  The tile's multiplier goes
+    // straight into the staging slot the epilogue reads it from.
+    if (p.act == ACT_MUL && elect_one()) {
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, local++) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const int as = local & 1;
+        mbar_wait(&mult_empty[as], ((local >> 1) & 1) ^ 1);
+        uint8_t* sm = stage_base + as * 2 * OUT_TILE_BYTES + OUT_TILE_BYTES;
+        const bool two = n0 + 64 < p.N;
+        mbar_expect_tx(&mult_full[as], two ? OUT_TILE_BYTES : OUT_HALF_BYTES);
+        tma_load_2d(sm, &map_pre, &mult_full[as], n0, m0);
+        if (two) tma_load_2d(sm + OUT_HALF_BYTES, &map_pre, &mult_full[as], n0 + 64, m0);
       }
     }
   } else if (warp == 1) {
@@ -245,6 +267,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bias_act_kernel(const __g
       // the TMA stores issued two tiles ago (same staging buffer) must have finished READING it
       if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
       epi_bar();
+      if (p.act == ACT_MUL) {
+        // out = acc * mult (the fc2 input-gradient GEMM fused with the GELU backward: mult = gelu'(pre-activation)),
+        // column sums of out = the fc1 bias gradient
+        mbar_wait(&mult_full[as], aphase);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int sw = (((colq & 1) * 4 + j) ^ (r & 7)) * 16;
+          float fm[8], g[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(sp + sw), fm);
+#pragma unroll
+          for (int t = 0; t < 8; t++) g[t] = __uint_as_float(v[j * 8 + t]) * fm[t];
+          *reinterpret_cast<bf16x8*>(so + sw) = pack8(g);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        epi_bar();
+        if (threadIdx.x == 64) {
+          mbar_arrive(&mult_empty[as]);  // every epilogue thread is past its multiplier reads
+          tma_store_2d(&map_out, stage_out, n0, m0);
+          if (n0 + 64 < p.N) tma_store_2d(&map_out, stage_out + OUT_HALF_BYTES, n0 + 64, m0);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+        {  // column sums over the staged bf16 tile: thread = (column pair, 16-row group); rows >= M hold zeros
+          const int te = threadIdx.x - 64, cp = te & 63, rg = te >> 6;
+          const uint8_t* base = stage_out + (cp >> 5) * OUT_HALF_BYTES + (cp & 3) * 4;
+          const int chunk = (cp & 31) >> 2;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int row = rg * 16 + i;
+            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((chunk ^ (row & 7)) * 16));
+            s0 += __uint_as_float(w2 << 16);
+            s1 += __uint_as_float(w2 & 0xffff0000u);
+          }
+          // into this CTA's PRIVATE row: all CTAs adding into one [N] vector serialise on its few cache lines in the
+          // L2 atomic units (N = 384 is 12 lines: measured 2x the whole kernel)
+          float* dst = p.colsum + (long long)blockIdx.x * p.N;
+          const int col = n0 + cp * 2;
+          if (col < p.N) atomicAdd(dst + col, s0);
+          if (col + 1 < p.N) atomicAdd(dst + col + 1, s1);
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 4; j++) {  // 4 chunks of 8 columns = 16 B
         const int cbase = n0 + colq * 32 + j * 8;
@@ -312,6 +376,39 @@ static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long lon
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// colsum[n] += sum over the CTAs' private rows
+__global__ void __launch_bounds__(256) colsum_fold_kernel(const float* __restrict__ ws, int rows, int N, float* __restrict__ colsum) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; r++) s += ws[(long long)r * N + n];
+  colsum[n] += s;
+}
+
+constexpr int MAX_GRID = 160;  // bound on the persistent grid = rows of the column-sum workspace
+
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mp,
+                  const Params& p, void* stream, int* grid_out = nullptr) {
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 4 * OUT_TILE_BYTES + (2 * STAGES + 8) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  int grid = esvit_num_sms();
+  if (grid > tiles) grid = tiles;
+  if (grid > MAX_GRID) grid = MAX_GRID;
+  if (p.act == ACT_MUL) {
+    cudaError_t e = cudaMemsetAsync(p.colsum, 0, (size_t)grid * p.N * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (grid_out) *grid_out = grid;
+  gemm_bias_act_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, mp, p);
+  ESVIT_LAUNCH_CHECK();
+}
+
 }  // namespace tg
 
 // out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]);  act: 0 identity, 1 exact GELU (then `pre`, if not NULL, receives
@@ -324,18 +421,26 @@ ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bia
   if (!tg::make_map(&mo, out, M, N, tg::BM) || !tg::make_map(&mp, (act && pre) ? pre : out, M, N, tg::BM))
     return ESVIT_ERR_BAD_ARG;
   tg::Params p;
-  p.out = (bf16*)out; p.pre = (bf16*)pre; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.act = act;
-  const size_t smem = (size_t)tg::STAGES * tg::STAGE_BYTES + 4 * tg::OUT_TILE_BYTES +
-                      (2 * tg::STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tg::gemm_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  const int tiles = (int)((M + tg::BM - 1) / tg::BM) * ((N + tg::BN - 1) / tg::BN);
-  int grid = esvit_num_sms();
-  if (grid > tiles) grid = tiles;
-  tg::gemm_bias_act_kernel<<<grid, tg::NUM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, mp, p);
+  p.out = (bf16*)out; p.pre = (bf16*)pre; p.bias = bias; p.colsum = nullptr; p.M = (int)M; p.N = N; p.K = K; p.act = act;
+  return tg::launch(ma, mb, mo, mp, p, stream);
+}
+
+// out[M,N] (bf16) = (a[M,K] @ w[N,K]^T) * mult[M,N];  colsum[N] (fp32) += column sums of out.
+// The input-gradient GEMM of fc2 fused with the GELU backward of fc1: a = dy, w = W2^T, mult = gelu'(pre-activation) as
+// saved by esvit_gemm_bias_act(act = 1), out = d(pre-activation), colsum = fc1 bias gradient (caller zero-fills);
+// ws fp32 [160 * N]: scratch for the per-CTA partial column sums.
+ESVIT_API int esvit_gemm_mul_colsum(const void* a, const void* w, const void* mult, void* out, float* colsum, float* ws,
+                                    long long M, int N, int K, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8) || M > 0x7fffffffLL || !mult || !colsum || !ws) return ESVIT_ERR_BAD_ARG;
+  CUtensorMap ma, mb, mo, mp;
+  if (!tg::make_map(&ma, a, M, K, tg::BM) || !tg::make_map(&mb, w, N, K, tg::BN)) return ESVIT_ERR_BAD_ARG;
+  if (!tg::make_map(&mo, out, M, N, tg::BM) || !tg::make_map(&mp, mult, M, N, tg::BM)) return ESVIT_ERR_BAD_ARG;
+  tg::Params p;
+  p.out = (bf16*)out; p.pre = nullptr; p.bias = nullptr; p.colsum = ws; p.M = (int)M; p.N = N; p.K = K;
+  p.act = tg::ACT_MUL;
+  int rows = 0;  // rows of ws in use = CTAs launched
+  const int rc = tg::launch(ma, mb, mo, mp, p, stream, &rows);
+  if (rc != 0) return rc;
+  tg::colsum_fold_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, rows, N, colsum);
   ESVIT_LAUNCH_CHECK();
 }

@@ -85,7 +85,10 @@ class SelfDistillStep:
         else:
             self.opt.zero_grad(set_to_none=True)
         ops.begin_step(loss.device)  # one zero-filled arena for all small gradient accumulators of this backward
-        loss.backward()
+        try:
+            loss.backward()
+        finally:
+            ops.end_step()
         if self.grad_allreduce and dist.is_initialized() and dist.get_world_size() > 1:
             grads = [p.grad for p in self.student.parameters() if p.grad is not None]
             flat = torch.cat([g.reshape(-1) for g in grads])  # one bandwidth-bound message (295 MB for Swin-T)

@@ -13,7 +13,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import _lib
+from . import _lib, shadow
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -34,13 +34,36 @@ class _Arena:
     fill kernels.  Regions are never handed out twice, so a stale arena is still correct (just smaller)."""
     buf: Optional[Tensor] = None
     off = 0
+    accs: Optional[dict] = None  # live only between begin_step() and end_step(): parameter -> its accumulator
 
 
 def begin_step(device, nfloats: int = 1 << 22) -> None:
-    """Call once per step before backward (engine.SelfDistillStep does); optional - without it ops fall back to
-    torch.zeros per accumulator."""
+    """Call right before ONE backward() (engine.SelfDistillStep does), end_step() right after; optional - without it
+    ops fall back to torch.zeros per accumulator."""
     _Arena.buf = torch.zeros(nfloats, dtype=F32, device=device)
     _Arena.off = 0
+    _Arena.accs = {}
+
+
+def end_step() -> None:
+    _Arena.accs = None
+
+
+def _acc(key, shape, device) -> Tuple[Tensor, bool]:
+    """Accumulated-gradient buffer of one parameter for THIS backward pass -> (buffer, first).  The backbone runs once per
+    resolution group (global / local crops) through the same weights; both backward kernels += into the same
+    zero-filled buffer and only the first call hands it to autograd (later calls return None for that input), so no
+    separate gradient-accumulation kernels run.  Valid because autograd holds the first tensor by reference until every
+    contribution to the leaf has been produced, and the kernels are ordered on one stream.  Outside
+    begin_step()/end_step() every call gets a fresh buffer."""
+    d = _Arena.accs
+    if d is None:
+        return _zeros(shape, device), True
+    t = d.get(key)
+    if t is not None and tuple(t.shape) == tuple(shape):
+        return t, False
+    t = d[key] = _zeros(shape, device)
+    return t.view(t.shape), True  # a fresh alias: autograd adopts it as .grad instead of cloning (sole reference)
 
 
 def _zeros(shape, device) -> Tensor:
@@ -112,10 +135,12 @@ class AddLayerNormFn(Function):
             g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
         dx = torch.empty_like(xout)
         ddelta = torch.empty(xout.shape, dtype=BF16, device=xout.device)
-        acc = _zeros((3, C), xout.device)  # dgamma | dbeta | ddelta_bias
+        acc, first = _acc(("add_ln", gamma.data_ptr()), (3, C), xout.device)  # dgamma | dbeta | ddelta_bias
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, _p(g_xout), _p(xout), _p(mean), _p(rstd),
                   _p(gamma), _p(keep), ctx.tps, _p(dx), _p(ddelta), _p(acc[0]), _p(acc[1]),
                   _p(acc[2]) if ctx.has_dbias else None, T, C, _stream())
+        if not first:
+            return dx, ddelta, None, None, None, None, None, None
         return dx, ddelta, (acc[2] if ctx.has_dbias else None), None, acc[0], acc[1], None, None
 
 
@@ -138,10 +163,10 @@ class LayerNormFn(Function):
         T, C = x.numel() // x.shape[-1], x.shape[-1]
         g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
         dx = torch.empty_like(x)
-        acc = _zeros((2, C), x.device)
+        acc, first = _acc(("ln", gamma.data_ptr()), (2, C), x.device)
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, None, _p(x), _p(mean), _p(rstd), _p(gamma),
                   None, 1, _p(dx), None, _p(acc[0]), _p(acc[1]), None, T, C, _stream())
-        return dx, acc[0], acc[1], None, None
+        return (dx, acc[0], acc[1], None, None) if first else (dx, None, None, None, None)
 
 
 class ResidualAddFn(Function):
@@ -155,6 +180,7 @@ class ResidualAddFn(Function):
         xout, _, _, _ = _add_ln_fwd(x, delta, keep, tps, None, None, 0.0, False, False)
         ctx.save_for_backward(keep)
         ctx.tps, ctx.has_dbias = tps, dbias is not None
+        ctx.dbias_ptr = dbias.data_ptr() if dbias is not None else 0
         return xout
 
     @staticmethod
@@ -164,10 +190,10 @@ class ResidualAddFn(Function):
         g = _chk(g, F32, "g")
         T, C = g.numel() // g.shape[-1], g.shape[-1]
         ddelta = torch.empty(g.shape, dtype=BF16, device=g.device)
-        db = _zeros((C,), g.device) if ctx.has_dbias else None
+        db, first = _acc(("res", ctx.dbias_ptr), (C,), g.device) if ctx.has_dbias else (None, True)
         _lib.call("esvit_add_ln_bwd", None, 0, _p(g), None, None, None, None, _p(keep), ctx.tps, None, _p(ddelta),
                   None, None, _p(db), T, C, _stream())
-        return g, ddelta, db, None
+        return g, ddelta, (db if first else None), None
 
 
 def add_layer_norm(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor], gamma: Tensor, beta: Tensor,
@@ -209,11 +235,11 @@ class PatchMergeLNFn(Function):
         B, L, C = x.shape
         g = _chk(g, BF16, "g")
         dx = torch.empty_like(x)
-        acc = _zeros((2, gamma.numel()), x.device)
+        acc, first = _acc(("merge", gamma.data_ptr()), (2, gamma.numel()), x.device)
         dgamma, dbeta = acc[0], acc[1]
         _lib.call("esvit_patch_merge_ln_bwd", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma),
                   _p(dbeta), B, H, W, C, _stream())
-        return dx, dgamma, dbeta, None, None, None
+        return (dx, dgamma, dbeta, None, None, None) if first else (dx, None, None, None, None, None)
 
 
 class TokenMeanFn(Function):
@@ -265,12 +291,12 @@ class PatchEmbedFn(Function):
         B, _, H, W = img.shape
         E = w.shape[0]
         g = _chk(g, F32, "g")
-        dw = _zeros(tuple(w.shape), w.device)
-        acc = _zeros((3, E), w.device)
+        dw, first = _acc(("pe_w", w.data_ptr()), tuple(w.shape), w.device)
+        acc, _ = _acc(("pe_b", w.data_ptr()), (3, E), w.device)
         db, dgamma, dbeta = acc[0], acc[1], acc[2]
         _lib.call("esvit_patch_embed_bwd", _p(img), _p(w), _p(bias), _p(gamma), _p(mean), _p(rstd), _p(g), _p(dw),
                   _p(db), _p(dgamma), _p(dbeta), B, H, W, E, _stream())
-        return None, dw, db, dgamma, dbeta, None
+        return (None, dw, db, dgamma, dbeta, None) if first else (None, None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -290,7 +316,9 @@ class WindowAttentionFn(Function):
         B, L, C3 = qkv.shape
         C = C3 // 3
         assert L == H * W
-        qb = qkv_bias.to(BF16)
+        qb = shadow.lookup(qkv_bias)  # optimiser-maintained bf16 copy (no cast kernel per call) when registered
+        if qb is None:
+            qb = qkv_bias.detach().to(BF16)
         nwin = B * (-(-H // ws)) * (-(-W // ws))
         out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
         lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
@@ -308,12 +336,12 @@ class WindowAttentionFn(Function):
         B, H, W, C, nH, ws, shift, scale = ctx.geo
         g = _chk(g, BF16, "g")
         dqkv = torch.empty_like(qkv)
-        dtable = _zeros(tuple(bias_table.shape), qkv.device)
-        dqb = _zeros((3 * C,), qkv.device)
+        dtable, first = _acc(("attn_t", bias_table.data_ptr()), tuple(bias_table.shape), qkv.device)
+        dqb, _ = _acc(("attn_b", bias_table.data_ptr()), (3 * C,), qkv.device)
         bws = torch.empty(nH * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
         _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(g), _p(lse), _p(dqkv),
                   _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
-        return dqkv, dqb, dtable, None, None, None, None, None, None
+        return dqkv, (dqb if first else None), (dtable if first else None), None, None, None, None, None, None
 
 
 class GeluFn(Function):
@@ -345,7 +373,7 @@ class BiasGeluFn(Function):
         y = torch.empty_like(x)
         _lib.call("esvit_gelu_fwd", _p(x), _p(y), x.numel(), _stream())
         ctx.save_for_backward(x)
-        ctx.bias_meta = (bias.shape, bias.device)
+        ctx.bias_meta = (bias.shape, bias.device, bias.data_ptr())
         return y
 
     @staticmethod
@@ -355,9 +383,9 @@ class BiasGeluFn(Function):
         g = _chk(g, BF16, "g")
         N = x.shape[-1]
         dx = torch.empty_like(x)
-        db = _zeros(tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
+        db, first = _acc(("bias", ctx.bias_meta[2]), tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
         _lib.call("esvit_gelu_bwd_dbias", _p(x), _p(g), _p(dx), _p(db), x.numel() // N, N, _stream())
-        return dx, db
+        return dx, (db if first else None)
 
 
 def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, want_pre: bool = False):
@@ -383,7 +411,7 @@ class LinearGeluFn(Function):
     def forward(ctx, x, w, bias):
         out, pre = gemm_bias_act(x, w, bias, act=1, want_pre=True)
         ctx.save_for_backward(x, w, pre)
-        ctx.bias_meta = (bias.shape, bias.device)
+        ctx.bias_meta = (bias.shape, bias.device, bias.data_ptr())
         return out
 
     @staticmethod
@@ -393,12 +421,50 @@ class LinearGeluFn(Function):
         g = _chk(g, BF16, "g")
         N = pre.shape[-1]
         dh = torch.empty_like(pre)
-        db = _zeros(tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
+        db, first = _acc(("bias", ctx.bias_meta[2]), tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
         _lib.call("esvit_mul_bwd_dbias", _p(pre), _p(g), _p(dh), _p(db), pre.numel() // N, N, _stream())
         dh2 = dh.reshape(-1, N)
         dx = (dh2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
         dw = dh2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
-        return dx, dw, db
+        return dx, dw, (db if first else None)
+
+
+GEMM_COLSUM_WS_ROWS = 160  # include/esvit_b200.h: esvit_gemm_mul_colsum scratch rows
+
+
+class MlpFn(Function):
+    """fc2(gelu(fc1(x))) of the Swin MLP (models/swin_transformer.py:31-35) with both GELU passes inside tcgen05 GEMM
+    epilogues.  forward: h, gelu' = esvit_gemm_bias_act(x, w1, b1) (one kernel), y = h @ w2^T + b2 (library GEMM).
+    backward: d(pre) = (dy @ w2) * gelu' and the fc1 bias gradient come out of ONE kernel (esvit_gemm_mul_colsum, w2t =
+    w2^T bf16 [4C, C]); the hidden-sized dh tensor of the unfused chain (GEMM -> multiply kernel) is never written.
+    fc2's bias gradient is produced by the consumer (residual add + LN backward), as for LinearBiasFn."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w2t):
+        h, pre = gemm_bias_act(x, w1, b1, act=1, want_pre=True)
+        with torch.autocast("cuda", enabled=False):
+            y = torch.nn.functional.linear(h, w2, b2)
+        ctx.save_for_backward(x, w1, pre, h, w2t)
+        ctx.bias_meta = (b1.shape, b1.device, b1.data_ptr())
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w1, pre, h, w2t = ctx.saved_tensors
+        g = _chk(g, BF16, "g")
+        C, N = g.shape[-1], pre.shape[-1]
+        g2 = g.reshape(-1, C)
+        M = g2.shape[0]
+        dw2 = g2.t() @ h.reshape(-1, N) if ctx.needs_input_grad[3] else None
+        dpre = torch.empty_like(pre)
+        db1, first = _acc(("bias", ctx.bias_meta[2]), tuple(ctx.bias_meta[0]), ctx.bias_meta[1])
+        ws = torch.empty(GEMM_COLSUM_WS_ROWS * N, dtype=F32, device=g.device)
+        _lib.call("esvit_gemm_mul_colsum", _p(g2), _p(w2t), _p(pre), _p(dpre), _p(db1), _p(ws), M, N, C, _stream())
+        d2 = dpre.reshape(-1, N)
+        dx = (d2 @ w1).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw1 = d2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
+        return dx, dw1, (db1 if first else None), dw2, None, None
 
 
 class LinearBiasFn(Function):

@@ -60,6 +60,14 @@ class _CastCache:
             t = self.d[k] = shadow.as_bf16(p)  # optimiser-maintained bf16 shadow when registered, else a cast
         return t
 
+    def transposed(self, p: Tensor) -> Tensor:
+        """bf16 W^T (contiguous) of a 2-D weight: the K-major operand of the fused input-gradient GEMM (ops.MlpFn)."""
+        k = ("T", id(p))
+        t = self.d.get(k)
+        if t is None:
+            t = self.d[k] = shadow.as_bf16(p, track_grad=False).t().contiguous()
+        return t
+
     def nograd(self, p: Tensor) -> Tensor:
         k = ("ng", id(p))
         t = self.d.get(k)
@@ -103,6 +111,10 @@ class Mlp(nn.Module):
         caller must route fc2.bias through the residual-add kernel (ops.add_layer_norm / residual_add delta_bias)."""
         if USE_TCGEN05_FC1:
             w1 = shadow.as_bf16(self.fc1.weight) if cc is None else cc(self.fc1.weight)
+            if torch.is_grad_enabled() and self.fc1.weight.requires_grad and self.fc2.bias is not None:
+                cc = cc if cc is not None else _CastCache()
+                return ops.MlpFn.apply(x, w1, self.fc1.bias, cc(self.fc2.weight), cc.nograd(self.fc2.bias),
+                                       cc.transposed(self.fc2.weight))
             h = ops.LinearGeluFn.apply(x, w1, self.fc1.bias)
         else:
             h = ops.BiasGeluFn.apply(_lin_c(x, self.fc1, cc), self.fc1.bias)

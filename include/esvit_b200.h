@@ -78,6 +78,14 @@ int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bi
  * TMA-staged 128B-swizzled tiles, tcgen05.mma with the fp32 accumulator in TMEM, persistent over output tiles. */
 int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M, int N, int K,
                         int act, void* stream);
+/* out[M,N] (bf16) = (a[M,K] @ w[N,K]^T) * mult[M,N]; colsum[N] (fp32) += column sums of out (caller zero-fills).
+ * Same kernel, third epilogue: the fc2 input-gradient GEMM (a = dy, w = W2^T) fused with the GELU backward of fc1
+ * (mult = gelu'(pre-activation) from esvit_gemm_bias_act act = 1) and the fc1 bias gradient - what autograd runs as
+ * mm + GeluBackward + sum(0) for Mlp.forward, models/swin_transformer.py:31-35.  The multiplier tile is TMA-loaded
+ * into the store-staging slot, so it is read once, coalesced, and never touches registers before use.
+ * ws fp32 [160*N]: caller-owned scratch (per-CTA partial column sums, folded into colsum inside the call). */
+int esvit_gemm_mul_colsum(const void* a, const void* w, const void* mult, void* out, float* colsum, float* ws,
+                          long long M, int N, int K, void* stream);
 
 /* ---- GELU (exact erf), bf16 ------------------------------------------------ models/swin_transformer.py:21-37 */
 int esvit_gelu_fwd(const void* x, void* y, long long n, void* stream);
