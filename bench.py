@@ -393,6 +393,19 @@ def main():
             torch.cuda.synchronize()
         with open(args.profile, "w") as f:
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        if os.environ.get("ESVIT_PROFILE_STACKS"):  # who launches the small ATen copy / add / fill kernels
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=True, record_shapes=True) as prof2:
+                one_step(crops)
+                torch.cuda.synchronize()
+            rows = [e for e in prof2.key_averages(group_by_input_shape=True, group_by_stack_n=8)
+                    if e.key in ("aten::copy_", "aten::add_", "aten::add", "aten::fill_", "aten::zero_", "aten::cat",
+                                 "aten::clone", "aten::contiguous", "aten::sum")]
+            rows.sort(key=lambda e: -e.count)
+            with open(args.profile + ".stacks.txt", "w") as f:
+                for e in rows[:60]:
+                    f.write(f"{e.key} x{e.count} cuda_total={e.device_time_total:.0f}us shapes={e.input_shapes}\n")
+                    for fr in e.stack[:8]:
+                        f.write(f"      {fr}\n")
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -27,8 +27,9 @@ SIGNATURES = {
     "esvit_token_mean_bwd": [P, P, P, I, I, I, P],
     "esvit_patch_embed_fwd": [P, P, P, P, P, F, P, P, P, I, I, I, I, P],
     "esvit_patch_embed_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
-    "esvit_window_attn_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
-    "esvit_window_attn_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
+    "esvit_window_attn_expand_bias": [P, P, I, I, P],
+    "esvit_window_attn_fwd": [P, P, P, P, I, P, P, I, I, I, I, I, I, I, F, P],
+    "esvit_window_attn_bwd": [P, P, P, P, I, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     "esvit_gemm_bias_act": [P, P, P, P, P, L, I, I, I, P],
     "esvit_gemm_mul_colsum": [P, P, P, P, P, P, L, I, I, P],
     "esvit_gelu_fwd": [P, P, L, P],
@@ -100,7 +101,7 @@ def call(name: str, *args) -> None:
 
 # ---- instrumentation used by bench.py (launch counting; live CUDA-event timing of one entry point) --------------
 # kernels launched per call of each entry point (entries that launch more than one kernel are computed per call)
-_LAUNCHES = {"esvit_colsum": 2, "esvit_window_attn_fwd": 2, "esvit_window_attn_bwd": 2}  # (+ bias expansion)
+_LAUNCHES = {"esvit_colsum": 2, "esvit_gemm_mul_colsum": 2}  # GEMM + fold of the per-CTA column sums
 _launch_count = 0
 _timed_names = set()
 _timed_events = []

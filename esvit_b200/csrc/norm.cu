@@ -42,7 +42,8 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-// forward: xout = x + keep[b] * delta ; y = LN(xout) * gamma + beta
+// forward: xout = x + keep[b] * delta ; y = LN(xout) * gamma + beta   (x may be NULL = 0: xout = fp32(delta), the start
+// of a residual stream - PatchMerging's reduction output - without a separate cast kernel)
 template <int LPR, int NV, typename OutT>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
     const float* __restrict__ x, const bf16* __restrict__ delta,
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
       const int c = (i * LPR + l) * 4;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok && c < C) {
-        v[i] = Vec4IO<float>::ld(x + row * C + c);
+        if (x) v[i] = Vec4IO<float>::ld(x + row * C + c);
         if (delta) {
           const float4 d = Vec4IO<bf16>::ld(delta + row * C + c);
           v[i].x += ks * d.x; v[i].y += ks * d.y; v[i].z += ks * d.z; v[i].w += ks * d.w;

@@ -59,9 +59,20 @@ static cudaError_t opt_in_smem(K kernel, size_t smem) {
 // qkv bf16 [B,H,W,3C] = qkv GEMM output INCLUDING its bias (channel order [q|k|v][head][32]); qkv_bias bf16 [3C] is
 // what a padded slot holds; bias_table fp32 [(2ws-1)^2, nH]; bias_ws fp32 [nH*8192] scratch (ws 7: expanded
 // bias; ws 14 backward: bias-gradient accumulator); out bf16 [B,H,W,C]; lse fp32 [B*nW, nH, ws*ws]
+// ws = 7: expand the rel-pos bias table into bias_ws [nH][64][64] (log2 domain, -inf padding) once, for every attention
+// call of the step that uses this table (pass bias_ready = 1 to them).  ws = 14: nothing to do.
+ESVIT_API int esvit_window_attn_expand_bias(const float* bias_table, float* bias_ws, int nH, int ws, void* stream) {
+  if (nH <= 0 || (ws != 7 && ws != 14) || !bias_table) return ESVIT_ERR_BAD_ARG;
+  if (ws == 7) {
+    if (!bias_ws) return ESVIT_ERR_BAD_ARG;
+    wa::expand_bias7_kernel<<<nH, 256, 0, (cudaStream_t)stream>>>(bias_table, bias_ws, nH);
+  }
+  ESVIT_LAUNCH_CHECK();
+}
+
 ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws,
-                                    void* out, float* lse, int B, int H, int W, int C, int nH, int ws, int shift,
-                                    float scale, void* stream) {
+                                    int bias_ready, void* out, float* lse, int B, int H, int W, int C, int nH, int ws,
+                                    int shift, float scale, void* stream) {
   wa::Geo g;
   if (!wa::make_geo(g, B, H, W, C, nH, ws, shift)) return ESVIT_ERR_BAD_ARG;
   const int nwin = B * g.nWy * g.nWx;
@@ -70,7 +81,7 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
   const bf16* qb = (const bf16*)qkv_bias;
   if (ws == 7) {
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
-    wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
+    if (!bias_ready) wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
     const size_t smem = wa::fwd7_smem();
     const int gx = wa::windows_grid(nwin, nH, 16);  // persistent: ~4 waves of 4 resident CTAs per SM
     if (shift > 0)
@@ -95,7 +106,7 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
 // qkv-bias gradient: column sums of dq/dk/dv over all window slots, padded ones included) are ACCUMULATED into
 // (caller zero-fills).
 ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws,
-                                    const void* out, const void* dout, const float* lse, void* dqkv,
+                                    int bias_ready, const void* out, const void* dout, const float* lse, void* dqkv,
                                     float* dbias_table, float* dqkv_bias, int B, int H, int W, int C, int nH, int ws,
                                     int shift, float scale, void* stream) {
   wa::Geo g;
@@ -106,7 +117,7 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
   const bf16* qb = (const bf16*)qkv_bias;
   if (ws == 7) {
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
-    wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
+    if (!bias_ready) wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
     const size_t smem = wa::bwd7_smem();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<true>, smem);
     if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<false>, smem);

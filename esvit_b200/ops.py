@@ -94,13 +94,14 @@ def _chk(t: Optional[Tensor], dtype, name: str) -> Optional[Tensor]:
 
 
 def _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, want_y, y_bf16):
-    T, C = x.numel() // x.shape[-1], x.shape[-1]
-    xout = torch.empty_like(x) if delta is not None else None
+    ref = x if x is not None else delta  # x = None: xout = fp32(delta), the start of a residual stream
+    T, C = ref.numel() // ref.shape[-1], ref.shape[-1]
+    xout = torch.empty(ref.shape, dtype=F32, device=ref.device) if delta is not None else None
     y = mean = rstd = None
     if want_y:
-        y = torch.empty(x.shape, dtype=BF16 if y_bf16 else F32, device=x.device)
-        mean = torch.empty(T, dtype=F32, device=x.device)
-        rstd = torch.empty(T, dtype=F32, device=x.device)
+        y = torch.empty(ref.shape, dtype=BF16 if y_bf16 else F32, device=ref.device)
+        mean = torch.empty(T, dtype=F32, device=ref.device)
+        rstd = torch.empty(T, dtype=F32, device=ref.device)
     _lib.call("esvit_add_ln_fwd", _p(x), _p(delta), _p(keep), tps, _p(gamma), _p(beta), eps, _p(xout), _p(y),
               1 if y_bf16 else 0, _p(mean), _p(rstd), T, C, _stream())
     return (xout if delta is not None else x), y, mean, rstd
@@ -119,10 +120,11 @@ class AddLayerNormFn(Function):
         dbias = _chk(dbias, F32, "delta_bias")
         keep = _chk(keep, F32, "keep")
         gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
-        tps = x.numel() // x.shape[-1] // x.shape[0]
+        ref = x if x is not None else delta  # x = None: the stream starts here as fp32(delta) (after PatchMerging)
+        tps = ref.numel() // ref.shape[-1] // ref.shape[0]
         xout, y, mean, rstd = _add_ln_fwd(x, delta, keep, tps, gamma, beta, eps, True, y_bf16)
         ctx.save_for_backward(xout, mean, rstd, gamma, keep)
-        ctx.tps, ctx.y_bf16, ctx.has_dbias = tps, y_bf16, dbias is not None
+        ctx.tps, ctx.y_bf16, ctx.has_dbias, ctx.has_x = tps, y_bf16, dbias is not None, x is not None
         return xout, y
 
     @staticmethod
@@ -133,7 +135,7 @@ class AddLayerNormFn(Function):
         g_xout = _chk(g_xout, F32, "g_xout") if g_xout is not None else None
         if g_y is not None:
             g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
-        dx = torch.empty_like(xout)
+        dx = torch.empty_like(xout) if ctx.has_x else None
         ddelta = torch.empty(xout.shape, dtype=BF16, device=xout.device)
         acc, first = _acc(("add_ln", gamma.data_ptr()), (3, C), xout.device)  # dgamma | dbeta | ddelta_bias
         _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, _p(g_xout), _p(xout), _p(mean), _p(rstd),
@@ -200,7 +202,7 @@ def add_layer_norm(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor], g
                    eps: float, y_bf16: bool = True, delta_bias: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     if delta is None:
         return x, LayerNormFn.apply(x, gamma, beta, eps, y_bf16)
-    return AddLayerNormFn.apply(x, delta, delta_bias, keep, gamma, beta, eps, y_bf16)
+    return AddLayerNormFn.apply(x, delta, delta_bias, keep, gamma, beta, eps, y_bf16)  # x may be None: xout = fp32(delta)
 
 
 def residual_add(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor],
@@ -309,7 +311,8 @@ class WindowAttentionFn(Function):
     and receives the COMPLETE qkv-bias gradient from the backward kernel (column sums of dq/dk/dv)."""
 
     @staticmethod
-    def forward(ctx, qkv, qkv_bias, bias_table, H: int, W: int, num_heads: int, ws: int, shift: int, scale: float):
+    def forward(ctx, qkv, qkv_bias, bias_table, H: int, W: int, num_heads: int, ws: int, shift: int, scale: float,
+                bias_exp: Optional[Tensor]):
         qkv = _chk(qkv, BF16, "qkv")
         qkv_bias = _chk(qkv_bias, F32, "qkv_bias")
         bias_table = _chk(bias_table, F32, "relative_position_bias_table")
@@ -322,26 +325,41 @@ class WindowAttentionFn(Function):
         nwin = B * (-(-H // ws)) * (-(-W // ws))
         out = torch.empty(B, L, C, dtype=BF16, device=qkv.device)
         lse = torch.empty(nwin * num_heads * ws * ws, dtype=F32, device=qkv.device)
-        bws = torch.empty(num_heads * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)  # kernel workspace
-        _lib.call("esvit_window_attn_fwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(lse), B, H, W, C,
+        # bias_exp: the table already expanded for this step by expand_rel_pos_bias (shared by every call and by the
+        # backward); without it each call expands into its own scratch
+        ready = 1 if (bias_exp is not None and ws == 7) else 0
+        bws = bias_exp if ready else torch.empty(num_heads * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
+        _lib.call("esvit_window_attn_fwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), ready, _p(out), _p(lse), B, H, W, C,
                   num_heads, ws, shift, scale, _stream())
-        ctx.save_for_backward(qkv, qb, bias_table, out, lse)
+        ctx.save_for_backward(qkv, qb, bias_table, out, lse, bws if ready else None)
         ctx.geo = (B, H, W, C, num_heads, ws, shift, scale)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        qkv, qb, bias_table, out, lse = ctx.saved_tensors
+        qkv, qb, bias_table, out, lse, bias_exp = ctx.saved_tensors
         B, H, W, C, nH, ws, shift, scale = ctx.geo
+        ready = 1 if bias_exp is not None else 0
         g = _chk(g, BF16, "g")
         dqkv = torch.empty_like(qkv)
         dtable, first = _acc(("attn_t", bias_table.data_ptr()), tuple(bias_table.shape), qkv.device)
         dqb, _ = _acc(("attn_b", bias_table.data_ptr()), (3 * C,), qkv.device)
-        bws = torch.empty(nH * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
-        _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), _p(out), _p(g), _p(lse), _p(dqkv),
+        bws = bias_exp if ready else torch.empty(nH * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
+        _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), ready, _p(out), _p(g), _p(lse), _p(dqkv),
                   _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
-        return dqkv, (dqb if first else None), (dtable if first else None), None, None, None, None, None, None
+        return dqkv, (dqb if first else None), (dtable if first else None), None, None, None, None, None, None, None
+
+
+def expand_rel_pos_bias(bias_table: Tensor, num_heads: int, ws: int) -> Optional[Tensor]:
+    """ws = 7: the rel-pos bias table expanded ONCE for all attention calls (both crop groups, forward and backward) that
+    use it this step -> fp32 [nH*4096] to pass as WindowAttentionFn's bias_exp; ws = 14: None (staged per CTA)."""
+    if ws != 7:
+        return None
+    bias_table = _chk(bias_table.detach(), F32, "relative_position_bias_table")
+    bws = torch.empty(num_heads * 4096, dtype=F32, device=bias_table.device)
+    _lib.call("esvit_window_attn_expand_bias", _p(bias_table), _p(bws), num_heads, ws, _stream())
+    return bws
 
 
 class GeluFn(Function):

@@ -50,6 +50,19 @@ class _CastCache:
 
     def __init__(self):
         self.d: Dict[int, Tensor] = {}
+        self.drop_plan = None  # [(block id, drop_prob)] of the backbone in execution order (set by the backbone)
+        self.keep_prob = None  # device fp32 [2*nblk, 1]: 1 - drop_prob per DropPath call
+        self.group = 0         # resolution group being run
+        self._drop = {}        # (group, batch size) -> {block id: (k1, k2)}
+
+    def drop_keeps(self, batch: int, drop_prob: float, device, key):
+        tab = self._drop.get((self.group, batch))
+        if tab is None:  # one draw for every block of this resolution group
+            r = torch.rand(len(self.drop_plan) * 2, batch, dtype=torch.float32, device=device)
+            keeps = r.add_(self.keep_prob).floor_().div_(self.keep_prob)      # timm: floor(keep_prob + U) / keep_prob
+            tab = self._drop[(self.group, batch)] = {bid: (keeps[2 * i], keeps[2 * i + 1])
+                                                     for i, (bid, _) in enumerate(self.drop_plan)}
+        return tab[key]
 
     def __call__(self, p: Optional[Tensor]) -> Optional[Tensor]:
         if p is None:
@@ -67,6 +80,13 @@ class _CastCache:
         if t is None:
             t = self.d[k] = shadow.as_bf16(p, track_grad=False).t().contiguous()
         return t
+
+    def expanded_bias(self, table: Tensor, num_heads: int, ws: int) -> Optional[Tensor]:
+        """the rel-pos bias table expanded once per forward call (ops.expand_rel_pos_bias), shared by the crop groups."""
+        k = ("B", id(table))
+        if k not in self.d:
+            self.d[k] = ops.expand_rel_pos_bias(table, num_heads, ws)
+        return self.d[k]
 
     def nograd(self, p: Tensor) -> Tensor:
         k = ("ng", id(p))
@@ -93,6 +113,17 @@ def drop_path_keep(batch: int, drop_prob: float, training: bool, device) -> Opti
     keep_prob = 1.0 - drop_prob
     r = keep_prob + torch.rand(batch, dtype=torch.float32, device=device)
     return r.floor_().div_(keep_prob)
+
+
+def drop_path_keeps(batch: int, drop_prob: float, training: bool, device, cc, key):
+    """The two DropPath scales of one block (attention branch, MLP branch).  Same distribution as drop_path_keep; the
+    uniforms of ALL blocks of one backbone pass are drawn by one torch.rand and turned into scales by two kernels
+    (registered in the pass' _CastCache) instead of four tiny kernels per DropPath call (~100 launches per step)."""
+    if drop_prob == 0. or not training:
+        return None, None
+    if cc is None or cc.drop_plan is None:
+        return (drop_path_keep(batch, drop_prob, training, device), drop_path_keep(batch, drop_prob, training, device))
+    return cc.drop_keeps(batch, drop_prob, device, key)
 
 
 class Mlp(nn.Module):
@@ -153,8 +184,10 @@ class WindowAttention(nn.Module):
         """y = norm1(x) bf16 [B, H*W, C] in token order -> proj(attention) bf16 [B, H*W, C]; proj.bias gets its gradient
         from the residual-add kernel the caller routes it through."""
         qkv = _lin_c(y, self.qkv, cc)
+        ws = self.window_size[0]
+        bexp = None if cc is None else cc.expanded_bias(self.relative_position_bias_table, self.num_heads, ws)
         a = ops.WindowAttentionFn.apply(qkv, self.qkv.bias, self.relative_position_bias_table, H, W, self.num_heads,
-                                        self.window_size[0], shift, float(self.scale))
+                                        ws, shift, float(self.scale), bexp)
         return _lin_c(a, self.proj, cc)
 
     def forward(self, x: Tensor, mask: Optional[Tensor] = None):
@@ -189,16 +222,15 @@ class SwinTransformerBlock(nn.Module):
     def fused(self, x: Tensor, pending, cc: Optional[_CastCache] = None):
         """(x fp32 [B,L,C], pending=(delta bf16, keep, delta_bias) or None) -> (x, pending): the MLP branch's
         residual add (and fc2 bias) is deferred into the next fused add+LN."""
-        B, L, C = x.shape
-        H = W = int(math.sqrt(L))
         delta, keep, dbias = pending if pending is not None else (None, None, None)
+        B, L, C = (x if x is not None else delta).shape  # x None: the stream starts as fp32(delta) (after PatchMerging)
+        H = W = int(math.sqrt(L))
         x, y = ops.add_layer_norm(x, delta, keep, self.norm1.weight, self.norm1.bias, self.norm1.eps, delta_bias=dbias)
         a = self.attn.attend(y, H, W, self.shift_size, cc)
-        k1 = drop_path_keep(B, self.drop_prob, self.training, x.device)
+        k1, k2 = drop_path_keeps(B, self.drop_prob, self.training, x.device, cc, id(self))
         x, y = ops.add_layer_norm(x, a, k1, self.norm2.weight, self.norm2.bias, self.norm2.eps,
                                   delta_bias=self.attn.proj.bias)
         z = self.mlp.fused(y, cc)
-        k2 = drop_path_keep(B, self.drop_prob, self.training, x.device)
         return x, (z, k2, self.mlp.fc2.bias)
 
     def forward(self, x: Tensor):
@@ -218,8 +250,15 @@ class PatchMerging(nn.Module):
         """x fp32 [B, H*W, C] -> fp32 [B, H*W/4, 2C]."""
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
+        return self.fused(x, cc).float()
+
+    def fused(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
+        """-> bf16 [B, H*W/4, 2C]; the caller starts the next stage's fp32 residual stream from it inside the next
+        add+LN kernel (ops.add_layer_norm with x=None) instead of a separate cast pass."""
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
         y = ops.PatchMergeLNFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, H, W)
-        return _lin_c(y, self.reduction, cc).float()
+        return _lin_c(y, self.reduction, cc)
 
 
 class BasicLayer(nn.Module):
@@ -236,17 +275,20 @@ class BasicLayer(nn.Module):
                                  norm_layer=norm_layer) for i in range(depth)])
         self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample else None
 
-    def fused(self, x: Tensor, cc: Optional[_CastCache] = None):
-        pend = None
+    def fused(self, x: Optional[Tensor], cc: Optional[_CastCache] = None, pend=None):
+        """(x fp32 or None, pend) -> (x, pend).  After a downsample the stream is handed on as (None, (merged bf16, None,
+        None)): the next stage's first add+LN turns it into the fp32 residual."""
         for blk in self.blocks:
             x, pend = blk.fused(x, pend, cc)
         if self.downsample is not None:
             x = ops.residual_add(x, *pend)
-            return self.downsample(x, cc), None
+            return None, (self.downsample.fused(x, cc), None, None)
         return x, pend
 
     def forward(self, x: Tensor) -> Tensor:
         x, pend = self.fused(x.float())
+        if x is None:
+            return pend[0].float()
         return x if pend is None else ops.residual_add(x, *pend)
 
 
@@ -326,7 +368,7 @@ class SwinTransformer(nn.Module):
         x = self.patch_embed(x)
         pend = None
         for layer in self.layers:
-            x, pend = layer.fused(x, cc)
+            x, pend = layer.fused(x, cc, pend)
         delta, keep, dbias = pend if pend is not None else (None, None, None)
         _, x_region = ops.add_layer_norm(x, delta, keep, self.norm.weight, self.norm.bias, self.norm.eps,
                                          y_bf16=False, delta_bias=dbias)
@@ -334,6 +376,15 @@ class SwinTransformer(nn.Module):
         if self.use_dense_prediction:
             return pooled, x_region
         return pooled
+
+    def _keep_prob_column(self, device) -> Tensor:
+        """device fp32 [2*nblk, 1] of 1 - drop_prob (two DropPath calls per block), built once per device."""
+        cache = self.__dict__.setdefault("_kp_cache", {})
+        t = cache.get(device)
+        if t is None:
+            probs = [[1.0 - blk.drop_prob] for layer in self.layers for blk in layer.blocks for _ in range(2)]
+            t = cache[device] = torch.tensor(probs, dtype=torch.float32).to(device)
+        return t
 
     def forward_feature_maps(self, x: Tensor):
         d = self.use_dense_prediction
@@ -349,6 +400,9 @@ class SwinTransformer(nn.Module):
         if not isinstance(x, list):
             x = [x]
         cc = _CastCache()
+        if self.training:
+            cc.drop_plan = [(id(blk), blk.drop_prob) for layer in self.layers for blk in layer.blocks]
+            cc.keep_prob = self._keep_prob_column(x[0].device)
         groups, start = [], 0
         for i in range(1, len(x) + 1):
             if i == len(x) or x[i].shape[-1] != x[start].shape[-1]:
@@ -356,7 +410,8 @@ class SwinTransformer(nn.Module):
                 start = i
         if self.use_dense_prediction:
             cls_l, fea_l, npatch = [], [], []
-            for s, e in groups:
+            for gi, (s, e) in enumerate(groups):
+                cc.group = gi
                 pooled, region = self.forward_features(torch.cat(x[s:e]) if e - s > 1 else x[s], cc)
                 B, N, C = region.shape
                 cls_l.append(pooled)
@@ -365,7 +420,10 @@ class SwinTransformer(nn.Module):
             output_cls = torch.cat(cls_l) if len(cls_l) > 1 else cls_l[0]
             output_fea = torch.cat(fea_l) if len(fea_l) > 1 else fea_l[0]
             return self.head(output_cls), self.head_dense(output_fea), output_fea, npatch
-        outs = [self.forward_features(torch.cat(x[s:e]) if e - s > 1 else x[s], cc) for s, e in groups]
+        outs = []
+        for gi, (s, e) in enumerate(groups):
+            cc.group = gi
+            outs.append(self.forward_features(torch.cat(x[s:e]) if e - s > 1 else x[s], cc))
         return self.head(torch.cat(outs) if len(outs) > 1 else outs[0])
 
 

@@ -25,7 +25,8 @@ extern "C" {
 /* ---- residual add + LayerNorm ------------------------------------------------------------------------------
  * replaces: x = shortcut + drop_path(branch); y = norm(x)      models/swin_transformer.py:329-331, :283, :687
  * xout = x + keep[row / tokens_per_sample] * delta (delta/keep/xout may be NULL; delta = proj / fc2 GEMM output
- * including its bias); y = LN(xout) (y may be NULL).
+ * including its bias); y = LN(xout) (y may be NULL).  x may be NULL (= 0) when delta is given: xout = fp32(delta), the
+ * first LN after PatchMerging's reduction GEMM (:411-415) without a separate bf16 -> fp32 pass.
  * x fp32 [T,C]; delta bf16 [T,C]; keep fp32 [B]; y bf16 or fp32 [T,C]; mean/rstd fp32 [T] (saved for backward). */
 int esvit_add_ln_fwd(const float* x, const void* delta, const float* keep, int tokens_per_sample,
                      const float* gamma, const float* beta, float eps, float* xout, void* y, int y_is_bf16,
@@ -64,10 +65,14 @@ int esvit_patch_embed_bwd(const float* img, const float* w, const float* bias, c
  * [B*nWindows, nH, ws*ws].  ws in {7,14}; head_dim 32.
  * bias_ws fp32 [nH*8192]: caller-owned scratch (ws 7: the rel-pos bias expanded to [nH][64][64]; ws 14 backward: the
  * lane-expanded bias-gradient accumulator [nH][27][6][32], cleared and folded into dbias_table inside the call).
+ * bias_ready (ws 7): 1 = bias_ws already holds the expansion written by esvit_window_attn_expand_bias for this table
+ * (one expansion per table per step instead of one per call), 0 = the call expands it itself.
  * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] (complete qkv-bias gradient) ACCUMULATED. */
-int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws, void* out,
-                          float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale, void* stream);
-int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws,
+int esvit_window_attn_expand_bias(const float* bias_table, float* bias_ws, int nH, int ws, void* stream);
+int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws, int bias_ready,
+                          void* out, float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
+                          void* stream);
+int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws, int bias_ready,
                           const void* out, const void* dout, const float* lse, void* dqkv, float* dbias_table,
                           float* dqkv_bias, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
                           void* stream);

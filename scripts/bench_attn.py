@@ -20,7 +20,7 @@ for dbg in ("0", "1", "2"):
             bias = torch.randn(3 * C, device=d) * 0.1
             table = torch.randn(169, nH, device=d) * 0.2
             go = torch.randn(B, H * H, C, device=d).to(torch.bfloat16)
-            f = lambda: ops.WindowAttentionFn.apply(qkv, bias, table, H, H, nH, 7, shift, 32 ** -0.5)
+            f = lambda: ops.WindowAttentionFn.apply(qkv, bias, table, H, H, nH, 7, shift, 32 ** -0.5, None)
             out = f()
             out.backward(go)
             torch.cuda.synchronize()

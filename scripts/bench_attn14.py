@@ -20,7 +20,7 @@ for generic in ("0",):
         bias = torch.randn(3 * C, device=d) * 0.1
         table = torch.randn(27 * 27, nH, device=d) * 0.2
         go = torch.randn(B, H * H, C, device=d).to(torch.bfloat16)
-        f = lambda: ops.WindowAttentionFn.apply(qkv, bias, table, H, H, nH, 14, shift, 32 ** -0.5)
+        f = lambda: ops.WindowAttentionFn.apply(qkv, bias, table, H, H, nH, 14, shift, 32 ** -0.5, None)
         out = f()
         out.backward(go)
         torch.cuda.synchronize()

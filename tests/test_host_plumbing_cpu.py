@@ -1,0 +1,67 @@
+"""Host-side autograd plumbing of the module mirror, exercised WITHOUT a GPU: every C-ABI call is replaced by a no-op
+(outputs stay uninitialised), so only the wiring is checked - fused pending residuals, the x-less add+LN after
+PatchMerging, the per-pass DropPath plan, the shared gradient accumulators of the two crop groups, MlpFn.  The numerics
+of the same paths are the -m gpu tests."""
+import torch
+
+from esvit_b200 import _lib, engine, ops
+
+
+def _patch(monkeypatch):
+    monkeypatch.setattr(_lib, "call", lambda name, *a: None)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+
+    def chk(t, dtype, name):
+        if t is None:
+            return None
+        assert t.dtype == dtype, (name, t.dtype, dtype)
+        return t if t.is_contiguous() else t.contiguous()
+
+    def gemm_bias_act(a, w, bias, act=0, want_pre=False):
+        out = torch.zeros(*a.shape[:-1], w.shape[0], dtype=torch.bfloat16)
+        return (out, torch.zeros_like(out)) if (act and want_pre) else out
+
+    monkeypatch.setattr(ops, "_chk", chk)
+    monkeypatch.setattr(ops, "gemm_bias_act", gemm_bias_act)
+
+
+def test_every_parameter_gets_one_gradient(monkeypatch):
+    _patch(monkeypatch)
+    spec = dict(engine.SWIN_SPECS["swin_tiny_w7"])
+    spec["depths"] = [1, 1, 2, 1]
+    torch.manual_seed(0)
+    net = engine.build_network(spec, 256, True, False, True, 224, None)
+    net.train()
+    B = 2
+    crops = [torch.randn(B, 3, 224, 224) for _ in range(2)] + [torch.randn(B, 3, 96, 96) for _ in range(3)]
+    cls, region, fea, npatch = net(crops)
+    assert cls.shape == (5 * B, 256) and npatch == [49, 9]
+    assert region.shape == (B * (2 * 49 + 3 * 9), 256) and fea.shape == (B * (2 * 49 + 3 * 9), 768)
+    loss = (cls.float() ** 2).sum() + (region.float() ** 2).sum()
+    ops.begin_step("cpu", 1 << 22)
+    try:
+        loss.backward()
+        n_shared = len(ops._Arena.accs)
+    finally:
+        ops.end_step()
+    assert ops._Arena.accs is None
+    assert n_shared > 20  # LN / bias / rel-pos-table accumulators were shared by the two crop groups
+    missing = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing
+    for n, p in net.named_parameters():
+        if p.grad is not None:
+            assert p.grad.shape == p.shape and p.grad.dtype == torch.float32, n
+
+
+def test_accumulators_are_private_outside_a_step(monkeypatch):
+    _patch(monkeypatch)
+    a, first_a = ops._acc(("k", 1), (4,), "cpu")
+    b, first_b = ops._acc(("k", 1), (4,), "cpu")
+    assert first_a and first_b and a.data_ptr() != b.data_ptr()
+    ops.begin_step("cpu", 1 << 10)
+    try:
+        a, first_a = ops._acc(("k", 1), (4,), "cpu")
+        b, first_b = ops._acc(("k", 1), (4,), "cpu")
+        assert first_a and not first_b and a.data_ptr() == b.data_ptr()
+    finally:
+        ops.end_step()
