@@ -266,7 +266,8 @@ def main():
     # ---- roofline of the dominant kernel: CUDA events around each launch, in EAGER steps (events cannot be
     # recorded inside a replayed graph); these steps double as the warm-up the graph capture needs -------------
     _lib.reset_counters()
-    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_window_attn_bwd", "esvit_window_attn_fwd", "esvit_gemm_bias_act"])
+    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_window_attn_bwd", "esvit_window_attn_fwd", "esvit_gemm_bias_act",
+                            "esvit_gemm_mul_colsum"])
     n_eager = 3 if args.min_warmup >= 3 else 1
     for _ in range(n_eager):
         l = one_step(crops)
@@ -376,11 +377,17 @@ def main():
         # tcgen05 fc1 GEMM + bias + GELU: reads A (M*K) and W, writes out and gelu' (2*M*N) in bf16
         r_gemm = agg("esvit_gemm_bias_act", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
                      "tg::gemm_bias_act_kernel tcgen05 fc1+bias+GELU (all launches of a step)")
+        # same kernel, third epilogue (fc2 dgrad * gelu' + column sums): reads dy (M*K), W2^T, gelu' (M*N), writes d(pre) (M*N)
+        r_gemm2 = agg("esvit_gemm_mul_colsum", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
+                      "tg::gemm_bias_act_kernel tcgen05 fc2-dgrad*gelu'+colsum (all launches of a step)")
+        if r_gemm2:  # profiles/r01_v11_ncu_full_key_metrics.txt: stage-0 local-crop launch, M=294912 K=96 N=384
+            r_gemm2["traffic"] = {"ncu_launch": "gemm_bias_act_kernel act=2 grid 148: M=294912, K=96, N=384",
+                                  "dram_bytes": 651.3e6, "algorithmic_bytes": 2 * (294912 * 96 + 384 * 96 + 2 * 294912 * 384)}
         if r_bwd and "w14" not in args.arch:
             # dram__bytes_read+write of one launch from `ncu --set full` (profiles/r01_final_ncu_full_key_metrics.txt)
             r_bwd["traffic"] = {"ncu_launch": "window_attn_bwd7_kernel<1> grid (6,296): stage-1 global crops, 100352 tokens x C=192",
                                 "dram_bytes": 278.3e6, "algorithmic_bytes": 16 * 100352 * 192}
-        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm) if r]
+        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm, r_gemm2) if r]
         if cands:
             cands.sort(key=lambda r: -r["ms_per_step"])
             roofline, roofline_others = cands[0], cands[1:]

@@ -12,7 +12,7 @@ done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "== smoke: $(tail -1 gpurun_out/smoke.log)"
 fi
-ESVIT_PROFILE_STACKS=1 timeout 900 python bench.py --steps 10 --warmup 3 --profile gpurun_out/prof_table.txt > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 900 python bench.py --steps 10 --warmup 3 --profile gpurun_out/prof_table.txt > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "== bench: $(tail -c 2500 gpurun_out/bench.json)"; tail -5 gpurun_out/bench.err
 if [ "$1" == "ncu" ]; then
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches.csv \
