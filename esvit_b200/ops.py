@@ -24,6 +24,11 @@ def _p(t: Optional[Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _po(t: Tensor, off_elems: int):
+    """pointer to element `off_elems` of a contiguous tensor (one resolution group inside a concatenated buffer)"""
+    return ctypes.c_void_p(t.data_ptr() + off_elems * t.element_size())
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -349,6 +354,123 @@ class WindowAttentionFn(Function):
         _lib.call("esvit_window_attn_bwd", _p(qkv), _p(qb), _p(bias_table), _p(bws), ready, _p(out), _p(g), _p(lse), _p(dqkv),
                   _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift, scale, _stream())
         return dqkv, (dqb if first else None), (dtable if first else None), None, None, None, None, None, None, None
+
+
+class WindowAttentionGroupsFn(Function):
+    """WindowAttentionFn over several resolution groups stored back to back in ONE token-major tensor: qkv bf16
+    [T, 3C], group g = (B, H, W, row0) = rows [row0, row0 + B*H*W) holding B maps of H x W tokens.  One kernel launch
+    per group on pointer offsets (no slicing / concatenation copies); the table / qkv-bias gradients of all groups
+    accumulate into the same buffers."""
+
+    @staticmethod
+    def forward(ctx, qkv, qkv_bias, bias_table, groups, num_heads: int, ws: int, shift: int, scale: float, bias_exp):
+        qkv = _chk(qkv, BF16, "qkv")
+        qkv_bias = _chk(qkv_bias, F32, "qkv_bias")
+        bias_table = _chk(bias_table, F32, "relative_position_bias_table")
+        T, C3 = qkv.shape
+        C = C3 // 3
+        assert sum(B * H * W for B, H, W, _ in groups) == T
+        qb = shadow.lookup(qkv_bias)
+        if qb is None:
+            qb = qkv_bias.detach().to(BF16)
+        out = torch.empty(T, C, dtype=BF16, device=qkv.device)
+        lse_off, n = [], 0
+        for B, H, W, _ in groups:
+            lse_off.append(n)
+            n += B * (-(-H // ws)) * (-(-W // ws)) * num_heads * ws * ws
+        lse = torch.empty(n, dtype=F32, device=qkv.device)
+        ready = 1 if (bias_exp is not None and ws == 7) else 0
+        bws = bias_exp if ready else torch.empty(num_heads * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
+        for (B, H, W, r0), lo in zip(groups, lse_off):
+            _lib.call("esvit_window_attn_fwd", _po(qkv, r0 * C3), _p(qb), _p(bias_table), _p(bws), ready, _po(out, r0 * C),
+                      _po(lse, lo), B, H, W, C, num_heads, ws, shift, scale, _stream())
+        ctx.save_for_backward(qkv, qb, bias_table, out, lse, bws if ready else None)
+        ctx.meta = (tuple(groups), tuple(lse_off), C, num_heads, ws, shift, scale)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        qkv, qb, bias_table, out, lse, bias_exp = ctx.saved_tensors
+        groups, lse_off, C, nH, ws, shift, scale = ctx.meta
+        g = _chk(g, BF16, "g")
+        ready = 1 if bias_exp is not None else 0
+        dqkv = torch.empty_like(qkv)
+        dtable, first = _acc(("attn_t", bias_table.data_ptr()), tuple(bias_table.shape), qkv.device)
+        dqb, _ = _acc(("attn_b", bias_table.data_ptr()), (3 * C,), qkv.device)
+        bws = bias_exp if ready else torch.empty(nH * ATTN_WS_FLOATS, dtype=F32, device=qkv.device)
+        for (B, H, W, r0), lo in zip(groups, lse_off):
+            _lib.call("esvit_window_attn_bwd", _po(qkv, r0 * 3 * C), _p(qb), _p(bias_table), _p(bws), ready, _po(out, r0 * C),
+                      _po(g, r0 * C), _po(lse, lo), _po(dqkv, r0 * 3 * C), _p(dtable), _p(dqb), B, H, W, C, nH, ws, shift,
+                      scale, _stream())
+        return dqkv, (dqb if first else None), (dtable if first else None), None, None, None, None, None, None
+
+
+class PatchMergeLNGroupsFn(Function):
+    """PatchMergeLNFn over resolution groups stored back to back: x fp32 [T, C] -> bf16 [T', 4C] (T' = sum of
+    B * ceil(H/2) * ceil(W/2)), one launch per group on pointer offsets."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, groups):
+        x, gamma, beta = _chk(x, F32, "x"), _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        T, C = x.shape
+        assert sum(B * H * W for B, H, W, _ in groups) == T
+        out_off, n = [], 0
+        for B, H, W, _ in groups:
+            out_off.append(n)
+            n += B * ((H + 1) // 2) * ((W + 1) // 2)
+        y = torch.empty(n, 4 * C, dtype=BF16, device=x.device)
+        mean = torch.empty(n, dtype=F32, device=x.device)
+        rstd = torch.empty(n, dtype=F32, device=x.device)
+        for (B, H, W, r0), o0 in zip(groups, out_off):
+            _lib.call("esvit_patch_merge_ln_fwd", _po(x, r0 * C), _p(gamma), _p(beta), eps, _po(y, o0 * 4 * C), _po(mean, o0),
+                      _po(rstd, o0), B, H, W, C, _stream())
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.meta = (tuple(groups), tuple(out_off))
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        groups, out_off = ctx.meta
+        T, C = x.shape
+        g = _chk(g, BF16, "g")
+        dx = torch.empty_like(x)
+        acc, first = _acc(("merge", gamma.data_ptr()), (2, gamma.numel()), x.device)
+        for (B, H, W, r0), o0 in zip(groups, out_off):
+            _lib.call("esvit_patch_merge_ln_bwd", _po(g, o0 * 4 * C), _po(x, r0 * C), _po(mean, o0), _po(rstd, o0), _p(gamma),
+                      _po(dx, r0 * C), _p(acc[0]), _p(acc[1]), B, H, W, C, _stream())
+        return (dx, acc[0], acc[1], None, None) if first else (dx, None, None, None, None)
+
+
+class TokenMeanGroupsFn(Function):
+    """TokenMeanFn over resolution groups stored back to back: region fp32 [T, C] -> pooled [sum B, C]."""
+
+    @staticmethod
+    def forward(ctx, region, groups):
+        region = _chk(region, F32, "region")
+        T, C = region.shape
+        nb = sum(B for B, _, _, _ in groups)
+        pooled = torch.empty(nb, C, dtype=F32, device=region.device)
+        b0 = 0
+        for B, H, W, r0 in groups:
+            _lib.call("esvit_token_mean_fwd", _po(region, r0 * C), _po(pooled, b0 * C), B, H * W, C, _stream())
+            b0 += B
+        ctx.meta = (tuple(groups), T, C)
+        return pooled
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        groups, T, C = ctx.meta
+        g = _chk(g, F32, "g")
+        d = torch.empty(T, C, dtype=F32, device=g.device)
+        b0 = 0
+        for B, H, W, r0 in groups:
+            _lib.call("esvit_token_mean_bwd", _po(g, b0 * C), None, _po(d, r0 * C), B, H * W, C, _stream())
+            b0 += B
+        return d, None
 
 
 def expand_rel_pos_bias(bias_table: Tensor, num_heads: int, ws: int) -> Optional[Tensor]:

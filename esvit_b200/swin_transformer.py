@@ -33,6 +33,10 @@ BF16 = torch.bfloat16
 
 # fc1 + bias + exact GELU as one tcgen05/TMA GEMM (esvit_gemm_bias_act) instead of library GEMM + GELU kernel
 USE_TCGEN05_FC1 = os.environ.get("ESVIT_TCGEN05_FC1", "1") != "0"
+# opt-in: run every per-token op (GEMMs, add+LN, MLP) ONCE over the concatenated tokens of all resolution groups of a
+# multi-crop forward instead of once per group; attention / patch merging / pooling launch per group on slices of the
+# same buffers (SwinTransformer._forward_fused_groups)
+USE_FUSED_GROUPS = os.environ.get("ESVIT_FUSE_GROUPS", "0") != "0"
 
 
 def _trunc_normal_(t: Tensor, std: float = .02) -> Tensor:
@@ -190,6 +194,15 @@ class WindowAttention(nn.Module):
                                         ws, shift, float(self.scale), bexp)
         return _lin_c(a, self.proj, cc)
 
+    def attend_groups(self, y: Tensor, grp, shift: int, cc: Optional[_CastCache] = None) -> Tensor:
+        """attend() for the concatenated tokens [T, C] of several resolution groups grp = [(B, H, W, row0)]."""
+        qkv = _lin_c(y, self.qkv, cc)
+        ws = self.window_size[0]
+        bexp = None if cc is None else cc.expanded_bias(self.relative_position_bias_table, self.num_heads, ws)
+        a = ops.WindowAttentionGroupsFn.apply(qkv, self.qkv.bias, self.relative_position_bias_table, tuple(grp),
+                                              self.num_heads, ws, shift, float(self.scale), bexp)
+        return _lin_c(a, self.proj, cc)
+
     def forward(self, x: Tensor, mask: Optional[Tensor] = None):
         """Reference signature: x [num_windows*B, N, C] pre-partitioned windows.  Only mask=None is supported
         standalone (the shifted case is handled inside SwinTransformerBlock from the geometry); the attention
@@ -233,6 +246,17 @@ class SwinTransformerBlock(nn.Module):
         z = self.mlp.fused(y, cc)
         return x, (z, k2, self.mlp.fc2.bias)
 
+    def fused_groups(self, x: Optional[Tensor], pending, grp, cc, k1: Optional[Tensor], k2: Optional[Tensor]):
+        """fused() over the concatenated tokens x fp32 [T, C] of the resolution groups grp = [(B, H, W, row0)];
+        k1 / k2: per-ROW DropPath scales (fp32 [T]) or None."""
+        delta, keep, dbias = pending if pending is not None else (None, None, None)
+        x, y = ops.add_layer_norm(x, delta, keep, self.norm1.weight, self.norm1.bias, self.norm1.eps, delta_bias=dbias)
+        a = self.attn.attend_groups(y, grp, self.shift_size, cc)
+        x, y = ops.add_layer_norm(x, a, k1, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                  delta_bias=self.attn.proj.bias)
+        z = self.mlp.fused(y, cc)
+        return x, (z, k2, self.mlp.fc2.bias)
+
     def forward(self, x: Tensor):
         """Reference signature: x [B, L, C] -> (x, attn); attn probabilities are not materialised (None)."""
         x, pend = self.fused(x.float(), None)
@@ -261,6 +285,17 @@ class PatchMerging(nn.Module):
         return _lin_c(y, self.reduction, cc)
 
 
+    def fused_groups(self, x: Tensor, grp, cc: Optional[_CastCache] = None):
+        """fused() over concatenated groups: x fp32 [T, C] -> (bf16 [T', 2C], the groups' new geometry)."""
+        y = ops.PatchMergeLNGroupsFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, tuple(grp))
+        new_grp, row0 = [], 0
+        for B, H, W, _ in grp:
+            Ho, Wo = (H + 1) // 2, (W + 1) // 2
+            new_grp.append((B, Ho, Wo, row0))
+            row0 += B * Ho * Wo
+        return _lin_c(y, self.reduction, cc), new_grp
+
+
 class BasicLayer(nn.Module):
     def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True,
                  qk_scale=None, drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None):
@@ -284,6 +319,19 @@ class BasicLayer(nn.Module):
             x = ops.residual_add(x, *pend)
             return None, (self.downsample.fused(x, cc), None, None)
         return x, pend
+
+    def fused_groups(self, x: Optional[Tensor], pend, grp, cc, keeps: Optional[Tensor]):
+        """fused() over concatenated groups; keeps: per-row DropPath scales fp32 [2*depth, T] of this layer or None."""
+        for i, blk in enumerate(self.blocks):
+            k1 = k2 = None
+            if keeps is not None and blk.drop_prob > 0. and blk.training:
+                k1, k2 = keeps[2 * i], keeps[2 * i + 1]
+            x, pend = blk.fused_groups(x, pend, grp, cc, k1, k2)
+        if self.downsample is not None:
+            x = ops.residual_add(x, *pend)
+            m, grp = self.downsample.fused_groups(x, grp, cc)
+            return None, (m, None, None), grp
+        return x, pend, grp
 
     def forward(self, x: Tensor) -> Tensor:
         x, pend = self.fused(x.float())
@@ -377,6 +425,53 @@ class SwinTransformer(nn.Module):
             return pooled, x_region
         return pooled
 
+    def _row_samples(self, grp, device) -> Tensor:
+        """int64 [T]: the (global) sample index of every token row of the concatenated groups (cached per geometry)."""
+        cache = self.__dict__.setdefault("_rs_cache", {})
+        key = (tuple(grp), device)
+        t = cache.get(key)
+        if t is None:
+            parts, b0 = [], 0
+            for B, H, W, _ in grp:
+                parts.append(torch.arange(b0, b0 + B, device=device).repeat_interleave(H * W))
+                b0 += B
+            t = cache[key] = torch.cat(parts)
+        return t
+
+    def _forward_fused_groups(self, x, groups, cc):
+        """Multi-crop forward with ONE pass over the concatenated tokens of all resolution groups for every per-token op
+        (same math and output order as the per-group loop of models/swin_transformer.py:713-763)."""
+        feats, grp, row0 = [], [], 0
+        for s, e in groups:
+            t = self.patch_embed(torch.cat(x[s:e]) if e - s > 1 else x[s])  # fp32 [B, L, E]
+            B, L, E = t.shape
+            H = W = int(math.sqrt(L))
+            feats.append(t.reshape(B * L, E))
+            grp.append((B, H, W, row0))
+            row0 += B * L
+        xa = torch.cat(feats) if len(feats) > 1 else feats[0]
+        dev = xa.device
+        keeps_all = None
+        if self.training and any(blk.drop_prob > 0. for layer in self.layers for blk in layer.blocks):
+            kp = self._keep_prob_column(dev)                                    # [2*nblk, 1]
+            r = torch.rand(kp.shape[0], sum(g[0] for g in grp), dtype=torch.float32, device=dev)
+            keeps_all = r.add_(kp).floor_().div_(kp)                            # timm DropPath scale per (call, sample)
+        pend, off = None, 0
+        for layer in self.layers:
+            depth = len(layer.blocks)
+            keeps = None
+            if keeps_all is not None:
+                keeps = keeps_all[2 * off:2 * (off + depth)].index_select(1, self._row_samples(grp, dev))
+            xa, pend, grp = layer.fused_groups(xa, pend, grp, cc, keeps)
+            off += depth
+        delta, keep, dbias = pend if pend is not None else (None, None, None)
+        _, x_region = ops.add_layer_norm(xa, delta, keep, self.norm.weight, self.norm.bias, self.norm.eps,
+                                         y_bf16=False, delta_bias=dbias)
+        pooled = ops.TokenMeanGroupsFn.apply(x_region, tuple(grp))
+        if self.use_dense_prediction:
+            return self.head(pooled), self.head_dense(x_region), x_region, [H * W for _, H, W, _ in grp]
+        return self.head(pooled)
+
     def _keep_prob_column(self, device) -> Tensor:
         """device fp32 [2*nblk, 1] of 1 - drop_prob (two DropPath calls per block), built once per device."""
         cache = self.__dict__.setdefault("_kp_cache", {})
@@ -408,6 +503,8 @@ class SwinTransformer(nn.Module):
             if i == len(x) or x[i].shape[-1] != x[start].shape[-1]:
                 groups.append((start, i))
                 start = i
+        if USE_FUSED_GROUPS:
+            return self._forward_fused_groups(x, groups, cc)
         if self.use_dense_prediction:
             cls_l, fea_l, npatch = [], [], []
             for gi, (s, e) in enumerate(groups):

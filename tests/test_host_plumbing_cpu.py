@@ -25,8 +25,14 @@ def _patch(monkeypatch):
     monkeypatch.setattr(ops, "gemm_bias_act", gemm_bias_act)
 
 
-def test_every_parameter_gets_one_gradient(monkeypatch):
+import pytest
+
+
+@pytest.mark.parametrize("fuse_groups", [False, True])
+def test_every_parameter_gets_one_gradient(monkeypatch, fuse_groups):
+    from esvit_b200 import swin_transformer
     _patch(monkeypatch)
+    monkeypatch.setattr(swin_transformer, "USE_FUSED_GROUPS", fuse_groups)
     spec = dict(engine.SWIN_SPECS["swin_tiny_w7"])
     spec["depths"] = [1, 1, 2, 1]
     torch.manual_seed(0)
@@ -45,7 +51,7 @@ def test_every_parameter_gets_one_gradient(monkeypatch):
     finally:
         ops.end_step()
     assert ops._Arena.accs is None
-    assert n_shared > 20  # LN / bias / rel-pos-table accumulators were shared by the two crop groups
+    assert n_shared > 20  # LN / bias / rel-pos-table accumulators (shared by the two crop groups when run per group)
     missing = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
     assert not missing, missing
     for n, p in net.named_parameters():
