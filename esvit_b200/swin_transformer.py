@@ -33,10 +33,10 @@ BF16 = torch.bfloat16
 
 # fc1 + bias + exact GELU as one tcgen05/TMA GEMM (esvit_gemm_bias_act) instead of library GEMM + GELU kernel
 USE_TCGEN05_FC1 = os.environ.get("ESVIT_TCGEN05_FC1", "1") != "0"
-# opt-in: run every per-token op (GEMMs, add+LN, MLP) ONCE over the concatenated tokens of all resolution groups of a
-# multi-crop forward instead of once per group; attention / patch merging / pooling launch per group on slices of the
-# same buffers (SwinTransformer._forward_fused_groups)
-USE_FUSED_GROUPS = os.environ.get("ESVIT_FUSE_GROUPS", "0") != "0"
+# run every per-token op (GEMMs, add+LN, MLP) ONCE over the concatenated tokens of all resolution groups of a multi-crop
+# forward instead of once per group; attention / patch merging / pooling launch per group on slices of the same buffers
+# (SwinTransformer._forward_fused_groups).  ESVIT_FUSE_GROUPS=0 restores the reference's per-group loop.
+USE_FUSED_GROUPS = os.environ.get("ESVIT_FUSE_GROUPS", "1") != "0"
 
 
 def _trunc_normal_(t: Tensor, std: float = .02) -> Tensor:
