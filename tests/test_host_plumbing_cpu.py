@@ -71,3 +71,21 @@ def test_accumulators_are_private_outside_a_step(monkeypatch):
         assert first_a and not first_b and a.data_ptr() == b.data_ptr()
     finally:
         ops.end_step()
+
+
+def test_group_geometry_of_the_concatenated_layout():
+    """rows -> samples map and the per-stage geometry the group-aware Functions receive (pure host logic)."""
+    spec = dict(engine.SWIN_SPECS["swin_tiny_w7"])
+    spec["depths"] = [1, 1, 1, 1]
+    net = engine.build_network(spec, 64, True, False, True, 224, None)
+    grp = [(2, 56, 56, 0), (3, 24, 24, 2 * 56 * 56)]
+    rs = net._row_samples(grp, torch.device("cpu"))
+    assert rs.numel() == 2 * 56 * 56 + 3 * 24 * 24
+    assert rs[0] == 0 and rs[56 * 56 - 1] == 0 and rs[56 * 56] == 1 and rs[2 * 56 * 56] == 2 and rs[-1] == 4
+    assert net._row_samples(grp, torch.device("cpu")) is rs  # cached per geometry
+    merged = []
+    row0 = 0
+    for B, H, W, _ in grp:  # what PatchMerging.fused_groups hands to the next stage
+        merged.append((B, (H + 1) // 2, (W + 1) // 2, row0))
+        row0 += B * ((H + 1) // 2) * ((W + 1) // 2)
+    assert merged == [(2, 28, 28, 0), (3, 12, 12, 2 * 28 * 28)]
