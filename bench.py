@@ -31,6 +31,21 @@ METRIC = "multi-crop images/sec, Swin-T W7 pretrain step (2 global 224^2 + 8 loc
 WORKLOAD = "swin_tiny_w7 2+8 crops DDINOLoss out_dim=65536 (BASELINE.json configs[1])"
 
 
+def attention_core_tflops(timed, n_eager):
+    """SURVEY.md 8(d) metric 2: algorithmic FLOPs of the attention core (QK^T + PV over the ws*ws slots of every window
+    the reference computes, padded ones included; head_dim 32) / measured kernel time, forward and backward separately
+    (backward = the standard 2.5x: recompute S, dP, dQ, dK, dV).  The QKV / proj GEMMs are separate kernels here."""
+    out = {}
+    for key, name, mult in (("fwd", "esvit_window_attn_fwd", 1.0), ("bwd", "esvit_window_attn_bwd", 2.5)):
+        sel = [t for t in timed if t["name"] == name and "windows" in t]
+        if not sel:
+            continue
+        flops = sum(mult * t["windows"] * t["nH"] * 2 * 2 * (t["ws"] ** 2) ** 2 * 32 for t in sel)
+        ms = sum(t["ms"] for t in sel)
+        out[key] = {"tflops": flops / (ms / 1e3) / 1e12, "gflop_per_step": flops / n_eager / 1e9, "ms_per_step": ms / n_eager}
+    return out
+
+
 def describe(args):
     """metric / workload strings; the defaults are BASELINE.json configs[1], other --arch values are parity-test configs."""
     if args.arch == "swin_tiny_w7" and args.local_crops == 8 and args.out_dim == 65536:
@@ -435,6 +450,10 @@ def main():
                           "l2": "per-step working set (>10 GB of activations/logits) >> 126 MB L2; no explicit flush"},
                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_others": roofline_others,
                "cpu_baseline": cpu_baseline, "loss": float(l)}
+        try:  # SURVEY.md 8(d) second metric; never allowed to break the contract line
+            out["window_attention_core"] = attention_core_tflops(timed, n_eager) if timed else None
+        except Exception as ex:  # noqa: BLE001
+            out["window_attention_core"] = {"error": repr(ex)}
         print(json.dumps(out), flush=True)
     # Hard exit on every rank: tearing the NCCL communicator down while CUDA graphs that captured collectives are
     # still alive can block forever (observed at N=2); all results are already reduced and printed.

@@ -108,11 +108,17 @@ _timed_events = []
 # algorithmic-bytes meta per timed entry point (bench.py roofline): extracted from the call's own arguments
 _META = {
     "esvit_dino_ce_bwd": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
-    "esvit_window_attn_bwd": lambda a: {"tokens": int(a[-9]) * int(a[-8]) * int(a[-7]), "C": int(a[-6])},
-    "esvit_window_attn_fwd": lambda a: {"tokens": int(a[-9]) * int(a[-8]) * int(a[-7]), "C": int(a[-6])},
+    "esvit_window_attn_bwd": lambda a: _attn_meta(a),
+    "esvit_window_attn_fwd": lambda a: _attn_meta(a),
     "esvit_gemm_bias_act": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7])},
     "esvit_gemm_mul_colsum": lambda a: {"M": int(a[6]), "N": int(a[7]), "K": int(a[8])},
 }
+
+
+def _attn_meta(a):
+    """(..., B, H, W, C, nH, ws, shift, scale, stream) of the window-attention entry points"""
+    B, H, W, C, nH, ws = (int(a[i]) for i in (-9, -8, -7, -6, -5, -4))
+    return {"tokens": B * H * W, "C": C, "nH": nH, "ws": ws, "windows": B * (-(-H // ws)) * (-(-W // ws))}
 
 
 def reset_counters() -> None:
