@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Usage (only where /root/reference exists):
 
-    python -m oracle.make_golden            # writes tests/golden/esvit_small_{dense,view}.pt
+    python -m oracle.make_golden            # writes tests/golden/esvit_small.pt and esvit_small_w14.pt
 
 The step loop below is main_esvit.py:541-590 driven through the reference's own
 modules (SwinTransformer.forward, DINOHead, DINOLoss/DDINOLoss, utils.clip_gradients,
@@ -27,15 +27,18 @@ from . import swin as S
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 SMALL = dict(img_size=112, embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), window_size=7)
+# ws = 14 geometry (Swin-S/B W14 configs): 112^2 -> 28x28 tokens = 2x2 windows of 14 (+ shift 7), then ONE un-shifted 14x14
+# window (:206-209), then 7x7; 48^2 local crops -> 12 / 6 / 3 tokens, i.e. heavily padded windows
+SMALL_W14 = dict(img_size=112, embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), window_size=14)
 HEAD = dict(hidden_dim=128, bottleneck_dim=64)
 K = 384
 HP = dict(lr=5e-4, weight_decay=0.04, clip_grad=3.0, freeze_last_layer=1, momentum_teacher=0.996,
           teacher_temp=0.04, student_temp=0.1, center_momentum=0.9)
 
 
-def build(dense: bool, seed: int = 0):
+def build(dense: bool, seed: int = 0, small=None):
     ns = R.load()
-    spec = S.SwinSpec(use_dense_prediction=dense, **SMALL)
+    spec = S.SwinSpec(use_dense_prediction=dense, **(small or SMALL))
     m = R.build_swin(spec, K, seed=seed)
     torch.manual_seed(seed + 1)
     with warnings.catch_warnings():
@@ -94,12 +97,15 @@ def stats(d):
     return {k: (float(v.double().sum()), float(v.double().norm())) for k, v in d.items()}
 
 
-def make(dense: bool, sd_init=None):
+def make(dense: bool, sd_init=None, small=None, compact: bool = False):
+    """compact: keep the initial state_dict, losses, gradient / parameter statistics and a few full gradients only (the
+    crops are regenerated from their seed)."""
+    small = small or SMALL
     R.ensure_process_group()
-    ns, spec, student = build(dense)
+    ns, spec, student = build(dense, small=small)
     if sd_init is not None:  # the view-only fixture shares the dense fixture's backbone + `head` weights
         student.load_state_dict({k: v for k, v in sd_init.items() if not k.startswith("head_dense")})
-    _, _, teacher = build(dense)
+    _, _, teacher = build(dense, small=small)
     teacher.load_state_dict(student.state_dict())
     for p in teacher.parameters():
         p.requires_grad = False
@@ -136,7 +142,7 @@ def make(dense: bool, sd_init=None):
 
     r0 = rec[0]
     out = dict(
-        meta=dict(spec=dict(SMALL, use_dense_prediction=dense), head=HEAD, out_dim=K, batch=B,
+        meta=dict(spec=dict(small, use_dense_prediction=dense), head=HEAD, out_dim=K, batch=B,
                   n_local=n_local if dense else 0, ncrops=ncrops, hp=HP, nsteps=nsteps,
                   crop_seed=1234, global_size=112, local_size=48,
                   generator="oracle/make_golden.py (reference run on CPU fp32, torch %s)" % torch.__version__),
@@ -147,6 +153,12 @@ def make(dense: bool, sd_init=None):
         grads_step0_stats=stats(r0["grads"]),
         grads_step0_full={k: r0["grads"][k] for k in FULL_GRADS if k in r0["grads"]},
     )
+    if compact:
+        so = r0["student_output"]
+        out.update(state_dict={k: v for k, v in sd0.items() if v.dtype.is_floating_point},  # index buffers = closed forms
+                   s_cls_stats=stats(dict(s_cls=so[0].detach(), s_region=so[1].detach(), s_fea=so[2].detach())),
+                   s_npatch=list(so[3]))
+        return out
     if dense:
         out.update(state_dict=sd0, crops=crops)
         so, to = r0["student_output"], r0["teacher_output"]
@@ -183,3 +195,7 @@ if __name__ == "__main__":
     path = os.path.join(OUT, "esvit_small.pt")
     torch.save(dict(dense=dense, view=view), path)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB; losses", dense["losses"], view["losses"])
+    w14 = make(True, small=SMALL_W14, compact=True)
+    path = os.path.join(OUT, "esvit_small_w14.pt")
+    torch.save(dict(dense=w14), path)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB; losses", w14["losses"])

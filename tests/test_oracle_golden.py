@@ -74,3 +74,35 @@ def test_closed_forms():
     assert torch.equal(rel.sum(-1), S.rel_pos_index(ws))
     m = S.shift_mask(6, 6, 7, 3)
     assert m.shape == (1, 49, 49) and float((m != 0).float().mean()) > 0.5
+
+
+def test_oracle_w14_training_steps_match_reference():
+    """ws = 14 geometry (Swin-S/B W14 configs: 2x2 shifted windows of 14, the single un-shifted 14x14 window of
+    :206-209, heavily padded local-crop windows): losses, gradients, teacher EMA and centers of two training steps of the
+    executed reference (tests/golden/esvit_small_w14.pt; crops regenerated from their seed)."""
+    import os
+
+    from helpers import GOLDEN
+    D = torch.load(os.path.join(os.path.dirname(GOLDEN), "esvit_small_w14.pt"), map_location="cpu", weights_only=False)["dense"]
+    M = D["meta"]
+    spec = S.SwinSpec(**M["spec"])
+    crops = ST.synthetic_crops(M["batch"], M["n_local"], seed=M["crop_seed"], global_size=M["global_size"],
+                               local_size=M["local_size"])
+    with torch.no_grad():
+        s = S.multicrop_forward(crops, D["state_dict"], spec)
+    assert s[3] == D["s_npatch"]
+    for a, k in zip(s[:3], ("s_cls", "s_region", "s_fea")):
+        ssum, nrm = D["s_cls_stats"][k]
+        assert abs(float(a.double().norm()) - nrm) < 1e-4 * nrm, k
+        assert abs(float(a.double().sum()) - ssum) < 1e-4 * nrm, k
+    orc = ST.OracleStep(D["state_dict"], spec, M["ncrops"], M["out_dim"], **M["hp"])
+    losses = [orc.step(crops, epoch=0, keep_grads=(i == 0)) for i in range(M["nsteps"])]
+    for a, b in zip(losses, D["losses"]):
+        assert abs(a - b) < 2e-5 * max(1.0, abs(b))
+    for k, g in D["grads_step0_full"].items():
+        assert torch.allclose(orc.grads_step[k], g, atol=1e-7 + 1e-4 * float(g.abs().max()), rtol=1e-3), k
+    for k, (ssum, nrm) in D["grads_step0_stats"].items():
+        assert abs(float(orc.grads_step[k].double().norm()) - nrm) < 1e-3 * nrm + 1e-9, k
+    assert torch.allclose(orc.center, D["center_after"], atol=1e-6)
+    for k, v in D["final_teacher_full"].items():
+        assert torch.allclose(orc.teacher[k], v, atol=1e-5), k
