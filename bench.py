@@ -73,6 +73,10 @@ def parse():
     ap.add_argument("--min-warmup", type=int, default=3, help="floor on warm-up steps (profiling runs lower it)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as a replayed CUDA graph")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the `gpu_reference` entry (the unmodified reference modules timed on the same GPUs)")
+    ap.add_argument("--gpu-ref-steps", type=int, default=10)
+    ap.add_argument("--gpu-ref-precisions", default="bf16,fp16")
     return ap.parse_args()
 
 
@@ -125,6 +129,29 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_ncu_traffic() -> dict:
+    """{kernel key: {"dram_bytes", "algorithmic_bytes", "ncu_launch", "commit"}} from profiles/ncu_traffic.json."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
+
+
+def cuda_parity_loss(arch: str, out_dim: int, n_local: int, batch: int, dev) -> float:
+    """first-step DDINO loss of the CUDA path on the cpu_baseline's inputs: same seed-0 random-init weights, same
+    seeded crops, DropPath 0, centers 0 (what oracle/step.py computes in its first step)."""
+    from esvit_b200 import engine
+    step, student, teacher, loss_mod = engine.make_step(arch=arch, out_dim=out_dim, ncrops=2 + n_local, dense=True,
+                                                        device=dev, drop_path=0.0, seed=0)
+    crops = [c.to(dev) for c in synthetic_crops(batch, n_local, 0)]
+    with torch.no_grad():
+        t = teacher(crops[:2])
+        s = student(crops)
+        l = float(loss_mod(s, t, 0, None))
+    del step, student, teacher, loss_mod
+    return l
 
 
 def synthetic_crops(batch: int, n_local: int, rank: int):
@@ -199,21 +226,22 @@ def cpu_reference_steps(arch: str, out_dim: int, n_local: int, batch: int, steps
     cores = pick_cpu_threads(sd, spec, crops) if device == "cpu" else 1
     torch.set_num_threads(cores)
     orc = ST.OracleStep(sd, spec, 2 + n_local, out_dim, device=device)
+    losses = []
     if device != "cpu":
         def run(n):
             for _ in range(n):
                 with torch.autocast("cuda", dtype=torch.bfloat16):
-                    orc.step(crops)
+                    losses.append(orc.step(crops))
             torch.cuda.synchronize()
     else:
         def run(n):
             for _ in range(n):
-                orc.step(crops)
+                losses.append(orc.step(crops))
     run(warmup)
     t0 = time.perf_counter()
     run(steps)
     dt = (time.perf_counter() - t0) / steps
-    return dt, cores
+    return dt, cores, losses
 
 
 def run_reference(args):
@@ -227,15 +255,31 @@ def run_reference(args):
         batch = args.ref_batch
     else:
         batch = args.batch
-    dt, cores = cpu_reference_steps(args.arch, args.out_dim, args.local_crops, batch, steps, warmup, device)
+    kind = "port"
+    if device != "cpu":
+        from baseline import reference_gpu as RG
+        if RG.available():  # the UNMODIFIED reference modules (baseline/_ref) through train_one_epoch's sequence
+            from esvit_b200.engine import SWIN_SPECS
+            torch.cuda.set_device(0)
+            dev = torch.device("cuda", 0)
+            crops = [c.to(dev) for c in synthetic_crops(batch, args.local_crops, 0)]
+            prec = args.gpu_ref_precisions.split(",")[0]
+            r = RG.time_reference(dict(SWIN_SPECS[args.arch]), args.out_dim, 2 + args.local_crops, crops, dev, prec, steps,
+                                  warmup, SWIN_SPECS[args.arch]["drop_path_rate"])
+            dt, cores, kind = r["ms_per_step"] / 1e3, 0, "reference"
+        else:
+            dt, cores, _ = cpu_reference_steps(args.arch, args.out_dim, args.local_crops, batch, steps, warmup, device)
+    else:
+        dt, cores, _ = cpu_reference_steps(args.arch, args.out_dim, args.local_crops, batch, steps, warmup, device)
     val = batch / dt
     sample = f"{steps} steps of batch {batch} ({WORKLOAD}), fp32, oracle port (oracle/step.py), {cores} threads" \
-        if device == "cpu" else f"{steps} steps of batch {batch}, oracle port eager on cuda with bf16 autocast"
+        if device == "cpu" else (f"{steps} steps of batch {batch}, " + ("unmodified reference modules (baseline/_ref) on cuda"
+                                 if kind == "reference" else "oracle port eager on cuda with bf16 autocast"))
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32" if device == "cpu" else "bf16", "data": "synthetic",
            "config": {"workload": WORKLOAD, "batch_per_step": batch, "device": device},
-           "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -395,13 +439,13 @@ def main():
         # same kernel, third epilogue (fc2 dgrad * gelu' + column sums): reads dy (M*K), W2^T, gelu' (M*N), writes d(pre) (M*N)
         r_gemm2 = agg("esvit_gemm_mul_colsum", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
                       "tg::gemm_bias_act_kernel tcgen05 fc2-dgrad*gelu'+colsum (all launches of a step)")
-        if r_gemm2:  # profiles/r01_v11_ncu_full_key_metrics.txt: stage-0 local-crop launch, M=294912 K=96 N=384
-            r_gemm2["traffic"] = {"ncu_launch": "gemm_bias_act_kernel act=2 grid 148: M=294912, K=96, N=384",
-                                  "dram_bytes": 651.3e6, "algorithmic_bytes": 2 * (294912 * 96 + 384 * 96 + 2 * 294912 * 384)}
-        if r_bwd and "w14" not in args.arch:
-            # dram__bytes_read+write of one launch from `ncu --set full` (profiles/r01_final_ncu_full_key_metrics.txt)
-            r_bwd["traffic"] = {"ncu_launch": "window_attn_bwd7_kernel<1> grid (6,296): stage-1 global crops, 100352 tokens x C=192",
-                                "dram_bytes": 278.3e6, "algorithmic_bytes": 16 * 100352 * 192}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures: read from the JSON that
+        # scripts/ncu_summarize.py wrote from the capture (with the commit it was taken at), never pasted in here
+        traffic = load_ncu_traffic()
+        for r, key in ((r_bwd, "window_attn_bwd"), (r_fwd, "window_attn_fwd"), (r_ce, "dino_ce_bwd"),
+                       (r_gemm, "gemm_bias_act"), (r_gemm2, "gemm_mul_colsum")):
+            if r and key in traffic:
+                r["traffic"] = traffic[key]
         cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm, r_gemm2) if r]
         if cands:
             cands.sort(key=lambda r: -r["ms_per_step"])
@@ -429,14 +473,60 @@ def main():
                     for fr in e.stack[:8]:
                         f.write(f"      {fr}\n")
 
-    cpu_baseline = None
+    from esvit_b200.engine import SWIN_SPECS
+    drop_path = SWIN_SPECS[args.arch]["drop_path_rate"]
+    parity_cuda = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del step, student, teacher, loss_mod
-        torch.cuda.empty_cache()
-        dt, cores = cpu_reference_steps(args.arch, args.out_dim, n_local, args.ref_batch, 3, 1)
+        parity_cuda = cuda_parity_loss(args.arch, args.out_dim, n_local, args.ref_batch, dev)
+
+    # free the product path (graphs first: they hold the captured NCCL work) before the reference arms run
+    own_mem_gib = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    last_loss = float(l)
+    del l
+    step._graphs.clear()
+    del step, student, teacher, loss_mod
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+    # ---- the reference's own PyTorch modules on the same GPU(s), same workload, same batch ------------------
+    gpu_reference = None
+    if not args.no_gpu_reference:
+        try:
+            from baseline import reference_gpu as RG
+            if not RG.available():
+                gpu_reference = {"unavailable": "baseline/_ref missing (run __graft_entry__.build() where /root/reference exists)"}
+            else:
+                runs = []
+                for prec in [x for x in args.gpu_ref_precisions.split(",") if x]:
+                    torch.cuda.reset_peak_memory_stats(dev)
+                    r = RG.time_reference(dict(SWIN_SPECS[args.arch]), args.out_dim, ncrops, crops, dev, prec,
+                                          args.gpu_ref_steps, 3, drop_path)
+                    r["value"] = world * B / (r["ms_per_step"] / 1e3)
+                    runs.append(r)
+                best = max(runs, key=lambda r: r["value"])
+                gpu_reference = {
+                    "what": "UNMODIFIED reference modules (models/swin_transformer.py, models/vision_transformer.py DINOHead, "
+                            "main_esvit.py DDINOLoss; baseline/_ref) driven through train_one_epoch's sequence "
+                            "(main_esvit.py:507-598): autocast, DDP at N>1, per-parameter clip, torch AdamW, EMA loop",
+                    "same_config": True, "batch_per_gpu": B, "n_gpus": world, "unit": "images/s",
+                    "value": best["value"], "ms_per_step": best["ms_per_step"], "precision": best["precision"], "runs": runs,
+                    "speedup_value": value / best["value"],
+                    "speedup_e2e": (e2e["value"] / best["value"]) if e2e else None}
+        except Exception as ex:  # noqa: BLE001 - the reference arm must never take the product line down
+            gpu_reference = {"error": repr(ex)[:400]}
+
+    cpu_baseline, parity_check = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, cores, ol = cpu_reference_steps(args.arch, args.out_dim, n_local, args.ref_batch, 3, 1)
         cpu_baseline = {"value": args.ref_batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
                         "sample": f"3 steps (+1 warm-up) of batch {args.ref_batch} of the same workload, fp32, "
                                   f"oracle/step.py on {cores} host threads, {dt:.2f} s/step"}
+        tol = 5e-3
+        err = abs(parity_cuda - ol[0]) / abs(ol[0])
+        parity_check = {"what": f"first-step DDINO loss, batch {args.ref_batch}, seed-0 weights, DropPath 0: CUDA path vs CPU oracle",
+                        "cuda_loss": parity_cuda, "oracle_loss": ol[0], "rel_err": err, "tol": tol, "ok": bool(err < tol)}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
@@ -444,23 +534,30 @@ def main():
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": WORKLOAD, "arch": args.arch, "batch_per_gpu": B, "global_batch": B * world,
                           "crops": f"2x224^2 + {n_local}x96^2", "out_dim": args.out_dim, "parallelism": f"dp{world}",
-                          "drop_path": "yaml (0.1)",
+                          "drop_path": drop_path,
                           "optimizer": "esvit fused clip+AdamW+EMA" if args.optimizer == "fused" else "torch AdamW fused",
                           "cuda_graph": use_graph,
                           "l2": "per-step working set (>10 GB of activations/logits) >> 126 MB L2; no explicit flush"},
                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_others": roofline_others,
-               "cpu_baseline": cpu_baseline, "loss": float(l)}
+               "cpu_baseline": cpu_baseline, "parity_check": parity_check, "gpu_reference": gpu_reference,
+               "peak_mem_gib": own_mem_gib, "loss": last_loss}
         try:  # SURVEY.md 8(d) second metric; never allowed to break the contract line
             out["window_attention_core"] = attention_core_tflops(timed, n_eager) if timed else None
         except Exception as ex:  # noqa: BLE001
             out["window_attention_core"] = {"error": repr(ex)}
         print(json.dumps(out), flush=True)
-    # Hard exit on every rank: tearing the NCCL communicator down while CUDA graphs that captured collectives are
-    # still alive can block forever (observed at N=2); all results are already reduced and printed.
     sys.stdout.flush()
     sys.stderr.flush()
     if dist.is_initialized():
-        os._exit(0)
+        # orderly teardown: every CUDA graph that captured NCCL work was destroyed above (step._graphs.clear()) and the
+        # device is idle, so the communicator can be torn down.  A watchdog hard-exits only if NCCL still fails to return.
+        def _watchdog():
+            time.sleep(60)
+            os._exit(0)
+        threading.Thread(target=_watchdog, daemon=True).start()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -163,7 +163,6 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(OptList L, const float* 
                                                         int base) {
   const int ti = base + blockIdx.y;
   const long long n = L.n[blockIdx.y];
-  if ((long long)blockIdx.x * blockDim.x * 4 >= n) return;  // big tensors get many CTAs, tiny ones one
   float* p = L.p[blockIdx.y];
   const float* g = L.g[blockIdx.y];
   float* m = L.m[blockIdx.y];
@@ -171,6 +170,11 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(OptList L, const float* 
   float* k = L.k[blockIdx.y];
   bf16* sp = L.sp[blockIdx.y];
   bf16* sk = L.sk[blockIdx.y];
+  // 4 elements per thread only when every pointer allows 16-byte (shadows: 8-byte) accesses; gradient views into a flat
+  // bucket at an odd offset take the scalar path, where a thread owns ONE element per grid stride
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)k)) & 15) == 0 &&
+                   ((((uintptr_t)sp) | ((uintptr_t)sk)) & 7) == 0;
+  if ((long long)blockIdx.x * blockDim.x * (vec ? 4 : 1) >= n) return;  // big tensors get many CTAs, tiny ones one
   const float lr = hyper[0], wd0 = hyper[1], clip = hyper[7];
   const int flag = (int)state[2 * ti + 1];
   OptScalars c;
@@ -190,8 +194,6 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(OptList L, const float* 
   c.decay = 1.f - lr * wd;
   const bool has_k = k != nullptr;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)k)) & 15) == 0 &&
-                   ((((uintptr_t)sp) | ((uintptr_t)sk)) & 7) == 0;
   const long long n4 = vec ? n / 4 : 0;
   for (long long i = tid; i < n4; i += nt) {
     float4 pv = reinterpret_cast<float4*>(p)[i], mv = make_float4(0, 0, 0, 0), vv = mv, gv = mv, kv = mv;

@@ -89,11 +89,7 @@ class SelfDistillStep:
             loss.backward()
         finally:
             ops.end_step()
-        if self.grad_allreduce and dist.is_initialized() and dist.get_world_size() > 1:
-            grads = [p.grad for p in self.student.parameters() if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in grads])  # one bandwidth-bound message (295 MB for Swin-T)
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        self.reduce_gradients()
         if self.fused:
             self.opt.step()  # clip + AdamW + EMA, one sweep
         else:
@@ -102,6 +98,15 @@ class SelfDistillStep:
             utils.cancel_gradients_last_layer(epoch, self.student, self.freeze_last_layer)
             self.opt.step()
         return loss.detach()
+
+    def reduce_gradients(self) -> None:
+        """DDP's gradient AVG all-reduce (main_esvit.py:377) for the graph-captured step: no-op at world size 1."""
+        if not (self.grad_allreduce and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        grads = [p.grad for p in self.student.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])  # one bandwidth-bound message (295 MB for Swin-T)
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
     def __call__(self, images: Sequence[torch.Tensor], epoch: int, lr: float, wd: float, momentum: float) -> torch.Tensor:
         images = list(images)

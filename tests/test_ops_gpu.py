@@ -453,9 +453,12 @@ def test_clip_gradients_per_tensor():
         assert_close(a, b, 1e-5, "clipped grad")
 
 
-def test_fused_adamw_clip_ema_matches_reference_sequence():
+@pytest.mark.parametrize("misaligned", [False, True])
+def test_fused_adamw_clip_ema_matches_reference_sequence(misaligned):
     """esvit_adamw_ema_multi == utils.clip_gradients -> cancel last_layer grads -> torch.optim.AdamW.step -> EMA loop
-    (main_esvit.py:579-590) on a toy module, over 3 steps with changing lr / wd / momentum."""
+    (main_esvit.py:579-590) on a toy module, over 3 steps with changing lr / wd / momentum.  misaligned: the gradients
+    are views of ONE flat bucket at odd element offsets (DDP gradient_as_bucket_view style) -> the kernel's scalar path
+    must still update every element."""
     import torch.nn as nn
 
     from esvit_b200.optim import FusedAdamWEMA
@@ -488,8 +491,21 @@ def test_fused_adamw_clip_ema_matches_reference_sequence():
                  for n, p_ in ref_s.named_parameters() if p_.requires_grad}
         for n, p_ in ref_s.named_parameters():
             p_.grad = grads[n].clone() if n in grads else None
-        for n, p_ in s.named_parameters():
-            p_.grad = grads[n].clone().to(d) if n in grads else None
+        if misaligned:
+            flat = torch.zeros(sum(g_.numel() + 8 for g_ in grads.values()) + 8, device=d)
+            off = 1
+            for n, p_ in s.named_parameters():
+                if n in grads:
+                    view = flat[off:off + p_.numel()].view(p_.shape)
+                    view.copy_(grads[n])
+                    assert view.data_ptr() % 16 != 0
+                    p_.grad = view
+                    off = ((off + p_.numel() + 3) // 4) * 4 + 1  # every view starts 4 bytes past a 16-byte boundary
+                else:
+                    p_.grad = None
+        else:
+            for n, p_ in s.named_parameters():
+                p_.grad = grads[n].clone().to(d) if n in grads else None
         # reference sequence
         for i, pg in enumerate(ropt.param_groups):
             pg["lr"] = lr
