@@ -32,6 +32,10 @@ SIGNATURES = {
     "esvit_window_attn_bwd": [P, P, P, P, I, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     "esvit_gemm_bias_act": [P, P, P, P, P, L, I, I, I, P],
     "esvit_gemm_mul_colsum": [P, P, P, P, P, P, L, I, I, P],
+    "esvit_gemm_bf16": [P, P, P, P, P, L, I, I, I, I, I, I, P],
+    "esvit_gemm_mul_colsum2": [P, P, P, P, P, P, L, I, I, I, I, P],
+    "esvit_gemm_wgrad_ws_floats": [I, I],
+    "esvit_gemm_wgrad": [P, P, P, P, L, I, I, I, I, P],
     "esvit_gelu_fwd": [P, P, L, P],
     "esvit_gelu_bwd": [P, P, P, L, P],
     "esvit_gelu_bwd_dbias": [P, P, P, P, L, I, P],
@@ -101,7 +105,7 @@ def call(name: str, *args) -> None:
 
 # ---- instrumentation used by bench.py (launch counting; live CUDA-event timing of one entry point) --------------
 # kernels launched per call of each entry point (entries that launch more than one kernel are computed per call)
-_LAUNCHES = {"esvit_colsum": 2, "esvit_gemm_mul_colsum": 2}  # GEMM + fold of the per-CTA column sums
+_LAUNCHES = {"esvit_colsum": 2, "esvit_gemm_mul_colsum": 2, "esvit_gemm_mul_colsum2": 2, "esvit_gemm_wgrad": 2}  # GEMM + fold
 _launch_count = 0
 _timed_names = set()
 _timed_events = []
@@ -112,6 +116,10 @@ _META = {
     "esvit_window_attn_fwd": lambda a: _attn_meta(a),
     "esvit_gemm_bias_act": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7])},
     "esvit_gemm_mul_colsum": lambda a: {"M": int(a[6]), "N": int(a[7]), "K": int(a[8])},
+    "esvit_gemm_bf16": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7]), "b_mn": int(a[9]), "act": int(a[10]),
+                                  "pre": a[4] is not None and getattr(a[4], "value", None) is not None},
+    "esvit_gemm_mul_colsum2": lambda a: {"M": int(a[6]), "N": int(a[7]), "K": int(a[8])},
+    "esvit_gemm_wgrad": lambda a: {"T": int(a[4]), "N": int(a[5]), "K": int(a[6])},
 }
 
 

@@ -528,6 +528,9 @@ class BiasGeluFn(Function):
         return dx, (db if first else None)
 
 
+GEMM_COLSUM_WS_ROWS = 160  # include/esvit_b200.h: esvit_gemm_mul_colsum scratch rows
+
+
 def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, want_pre: bool = False):
     """tcgen05/TMA GEMM: act(a @ w^T + bias) -> bf16 [M, N] (and gelu'(a @ w^T + bias) when act != 0 and want_pre)."""
     a, w = _chk(a, BF16, "a"), _chk(w, BF16, "w")
@@ -539,6 +542,65 @@ def gemm_bias_act(a: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, wa
     pre = torch.empty_like(out) if (act and want_pre) else None
     _lib.call("esvit_gemm_bias_act", _p(a), _p(w), _p(bias), _p(out), _p(pre), M, N, K, act, _stream())
     return (out, pre) if (act and want_pre) else out
+
+
+def gemm(a: Tensor, b: Tensor, bias: Optional[Tensor] = None, act: int = 0, want_pre: bool = False, a_mn: bool = False,
+         b_mn: bool = False, tile: int = 0):
+    """Second-generation tcgen05 GEMM: act(opA(a) @ opB(b) + bias) -> bf16 [M, N].
+    a: [..., K] (a_mn: [K, M]);  b: [N, K] (b_mn: [K, N] - a Linear weight read as it lies for the input gradient)."""
+    a, b = _chk(a, BF16, "a"), _chk(b, BF16, "b")
+    bias = _chk(bias, F32, "bias")
+    if a_mn:
+        K, M = a.shape
+        lead = (M,)
+    else:
+        K = a.shape[-1]
+        M = a.numel() // K
+        lead = tuple(a.shape[:-1])
+    N = b.shape[1] if b_mn else b.shape[0]
+    assert (b.shape[0] if b_mn else b.shape[1]) == K, (a.shape, b.shape)
+    out = torch.empty(*lead, N, dtype=BF16, device=a.device)
+    pre = torch.empty_like(out) if (act and want_pre) else None
+    _lib.call("esvit_gemm_bf16", _p(a), _p(b), _p(bias), _p(out), _p(pre), M, N, K, 1 if a_mn else 0, 1 if b_mn else 0, act,
+              tile, _stream())
+    return (out, pre) if (act and want_pre) else out
+
+
+def gemm_mul_colsum(a: Tensor, b: Tensor, mult: Tensor, colsum: Tensor, b_mn: bool = False, tile: int = 0) -> Tensor:
+    """out = (a @ opB(b)) * mult (bf16); colsum (fp32 [N]) += column sums of out."""
+    a, b, mult = _chk(a, BF16, "a"), _chk(b, BF16, "b"), _chk(mult, BF16, "mult")
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = b.shape[1] if b_mn else b.shape[0]
+    out = torch.empty_like(mult)
+    ws = torch.empty(GEMM_COLSUM_WS_ROWS * N, dtype=F32, device=a.device)
+    _lib.call("esvit_gemm_mul_colsum2", _p(a), _p(b), _p(mult), _p(out), _p(colsum), _p(ws), M, N, K, 1 if b_mn else 0, tile,
+              _stream())
+    return out
+
+
+_wgrad_ws = {}
+
+
+def gemm_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False, tile: int = 0) -> Tensor:
+    """dw[N, K] (fp32) (+)= dy[T, N]^T @ x[T, K]: the weight gradient of a Linear straight in fp32 (no bf16 round trip,
+    no cast kernel, no transposes); deterministic split-K."""
+    dy, x = _chk(dy, BF16, "dy"), _chk(x, BF16, "x")
+    N, K = dy.shape[-1], x.shape[-1]
+    T = dy.numel() // N
+    assert x.numel() // K == T
+    if out is None:
+        out = torch.empty(N, K, dtype=F32, device=dy.device)
+        accumulate = False
+    key = (dy.device, N, K)
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        n = _lib.load().esvit_gemm_wgrad_ws_floats(N, K)
+        if n <= 0:
+            raise ValueError("esvit_gemm_wgrad: weight too large for the split-K workspace")
+        ws = _wgrad_ws[key] = torch.empty(n, dtype=F32, device=dy.device)
+    _lib.call("esvit_gemm_wgrad", _p(dy), _p(x), _p(out), _p(ws), T, N, K, 1 if accumulate else 0, tile, _stream())
+    return out
 
 
 class LinearGeluFn(Function):
@@ -569,7 +631,6 @@ class LinearGeluFn(Function):
         return dx, dw, (db if first else None)
 
 
-GEMM_COLSUM_WS_ROWS = 160  # include/esvit_b200.h: esvit_gemm_mul_colsum scratch rows
 
 
 class MlpFn(Function):

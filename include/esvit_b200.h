@@ -92,6 +92,24 @@ int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* o
 int esvit_gemm_mul_colsum(const void* a, const void* w, const void* mult, void* out, float* colsum, float* ws,
                           long long M, int N, int K, void* stream);
 
+/* ---- second-generation tcgen05 GEMM family (csrc/gemm2_tcgen05.cu): every nn.Linear of the step, forward, input
+ * gradient and weight gradient -------- models/swin_transformer.py:21-37,88-91,125,150,393-420; vision_transformer.py:385-418
+ * CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles) or single CTAs; operands K-major or MN-major (the same row-major
+ * matrices read "transposed" by TMA + UMMA MN-major descriptors: no transposed copies).
+ * gemm_bf16: out[M,N] (bf16) = act(opA(a) . opB(b) + bias[N]).  a: a_mn = 0 [M,K] | a_mn = 1 [K,M];  b: b_mn = 0 [N,K]
+ *   (Linear weight, forward) | b_mn = 1 [K,N] (Linear weight [out = K, in = N], input gradient).  act 0 identity, 1 exact
+ *   GELU (pre != NULL also receives gelu'(pre-activation)).  tile: 0 = automatic, else cta_group * 1000 + BN.
+ * gemm_mul_colsum2: out = (a . opB(b)) * mult, colsum ACCUMULATED (see esvit_gemm_mul_colsum); ws fp32 [160 * N].
+ * gemm_wgrad: dw[N,K] (fp32) (+)= dy[T,N]^T . x[T,K], split over T, deterministic fold of fp32 partial tiles held in ws
+ *   (esvit_gemm_wgrad_ws_floats(N, K) fp32 elements).  All of M / N / K / T multiples of 8. */
+int esvit_gemm_bf16(const void* a, const void* b, const float* bias, void* out, void* pre, long long M, int N, int K,
+                    int a_mn, int b_mn, int act, int tile, void* stream);
+int esvit_gemm_mul_colsum2(const void* a, const void* b, const void* mult, void* out, float* colsum, float* ws,
+                           long long M, int N, int K, int b_mn, int tile, void* stream);
+int esvit_gemm_wgrad_ws_floats(int N, int K);
+int esvit_gemm_wgrad(const void* dy, const void* x, float* dw, float* ws, long long T, int N, int K, int accumulate,
+                     int tile, void* stream);
+
 /* ---- GELU (exact erf), bf16 ------------------------------------------------ models/swin_transformer.py:21-37 */
 int esvit_gelu_fwd(const void* x, void* y, long long n, void* stream);
 int esvit_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream);
