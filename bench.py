@@ -348,7 +348,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        one_step(crops)
+        l = one_step(crops)
+        float(l)  # the loss is read back every step, as train_one_epoch does (main_esvit.py:546, :596): ranks stay in step
     e1.record()
     barrier_sync()
     clocks = sampler.stop() if rank == 0 else None
@@ -537,6 +538,7 @@ def main():
                           "drop_path": drop_path,
                           "optimizer": "esvit fused clip+AdamW+EMA" if args.optimizer == "fused" else "torch AdamW fused",
                           "cuda_graph": use_graph,
+                          "timed_loop": "loss.item() every step (main_esvit.py:546,596)",
                           "l2": "per-step working set (>10 GB of activations/logits) >> 126 MB L2; no explicit flush"},
                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_others": roofline_others,
                "cpu_baseline": cpu_baseline, "parity_check": parity_check, "gpu_reference": gpu_reference,

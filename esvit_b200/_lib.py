@@ -43,7 +43,7 @@ SIGNATURES = {
     "esvit_l2norm_fwd": [P, P, P, F, L, I, P],
     "esvit_l2norm_bwd": [P, P, P, P, L, I, P],
     "esvit_weight_norm_fwd": [P, P, P, P, L, I, P],
-    "esvit_weight_norm_bwd": [P, P, P, P, P, P, L, I, P],
+    "esvit_weight_norm_bwd": [P, P, P, P, I, P, P, L, I, P],
     "esvit_row_lse": [P, P, F, P, L, I, P],
     "esvit_dino_ce_fwd": [P, P, P, P, P, P, F, F, P, L, I, P],
     "esvit_dino_ce_bwd": [P, P, P, P, P, P, P, P, F, F, P, L, I, P],

@@ -211,10 +211,19 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const float* __res
   }
 }
 
-// dv = (g/n) * (dw - v * <dw,v>/n^2) ; dg = <dw,v>/n
+// dv = (g/n) * (dw - v * <dw,v>/n^2) ; dg = <dw,v>/n.   DW = bf16 (library-GEMM gradient) or float (esvit_gemm_wgrad)
+__device__ __forceinline__ float4 load4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 d0 = __bfloat1622float2(*reinterpret_cast<bf162*>(&u.x));
+  float2 d1 = __bfloat1622float2(*reinterpret_cast<bf162*>(&u.y));
+  return make_float4(d0.x, d0.y, d1.x, d1.y);
+}
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <typename DW>
 __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                                               const float* __restrict__ norm_i,
-                                                              const bf16* __restrict__ dw, float* __restrict__ dv,
+                                                              const DW* __restrict__ dw, float* __restrict__ dv,
                                                               float* __restrict__ dg, long long K, int D) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -222,25 +231,21 @@ __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __res
   for (long long r = warp; r < K; r += nwarps) {
     float s = 0.f;
     for (int c = lane * 4; c < D; c += 128) {
-      float4 a = *reinterpret_cast<const float4*>(v + r * D + c);
-      uint2 u = *reinterpret_cast<const uint2*>(dw + r * D + c);
-      float2 d0 = __bfloat1622float2(*reinterpret_cast<bf162*>(&u.x));
-      float2 d1 = __bfloat1622float2(*reinterpret_cast<bf162*>(&u.y));
-      s += (a.x * d0.x + a.y * d0.y) + (a.z * d1.x + a.w * d1.y);
+      const float4 a = *reinterpret_cast<const float4*>(v + r * D + c);
+      const float4 d = load4(dw + r * D + c);
+      s += (a.x * d.x + a.y * d.y) + (a.z * d.z + a.w * d.w);
     }
     s = warp_sum(s);
     const float n = norm_i[r], gg = g[r];
     const float sc = gg / n, k2 = s / (n * n);
     for (int c = lane * 4; c < D; c += 128) {
-      float4 a = *reinterpret_cast<const float4*>(v + r * D + c);
-      uint2 u = *reinterpret_cast<const uint2*>(dw + r * D + c);
-      float2 d0 = __bfloat1622float2(*reinterpret_cast<bf162*>(&u.x));
-      float2 d1 = __bfloat1622float2(*reinterpret_cast<bf162*>(&u.y));
+      const float4 a = *reinterpret_cast<const float4*>(v + r * D + c);
+      const float4 d = load4(dw + r * D + c);
       float4 o;
-      o.x = sc * (d0.x - a.x * k2);
-      o.y = sc * (d0.y - a.y * k2);
-      o.z = sc * (d1.x - a.z * k2);
-      o.w = sc * (d1.y - a.w * k2);
+      o.x = sc * (d.x - a.x * k2);
+      o.y = sc * (d.y - a.y * k2);
+      o.z = sc * (d.z - a.z * k2);
+      o.w = sc * (d.w - a.w * k2);
       *reinterpret_cast<float4*>(dv + r * D + c) = o;
     }
     if (lane == 0 && dg) dg[r] = s / n;
@@ -327,10 +332,12 @@ ESVIT_API int esvit_weight_norm_fwd(const float* v, const float* g, void* w, flo
   ESVIT_LAUNCH_CHECK();
 }
 
-ESVIT_API int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, const void* dw, float* dv,
-                                    float* dg, long long K, int D, void* stream) {
+ESVIT_API int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, const void* dw, int dw_is_f32,
+                                    float* dv, float* dg, long long K, int D, void* stream) {
   if (D % 4 != 0 || K <= 0) return ESVIT_ERR_BAD_ARG;
-  weight_norm_bwd_kernel<<<ew_grid(K, 8, 16), 256, 0, (cudaStream_t)stream>>>(v, g, norm, (const bf16*)dw, dv, dg, K,
-                                                                               D);
+  if (dw_is_f32)
+    weight_norm_bwd_kernel<float><<<ew_grid(K, 8, 16), 256, 0, (cudaStream_t)stream>>>(v, g, norm, (const float*)dw, dv, dg, K, D);
+  else
+    weight_norm_bwd_kernel<bf16><<<ew_grid(K, 8, 16), 256, 0, (cudaStream_t)stream>>>(v, g, norm, (const bf16*)dw, dv, dg, K, D);
   ESVIT_LAUNCH_CHECK();
 }

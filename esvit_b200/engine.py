@@ -48,6 +48,62 @@ def build_network(spec: dict, out_dim: int, use_dense_prediction: bool, is_teach
     return net
 
 
+class _GradReducer:
+    """Bucketed gradient all-reduce overlapped with backward - what DistributedDataParallel does for the reference
+    (main_esvit.py:377), in a form that is captured inside the step's CUDA graph: parameters are bucketed in REVERSE
+    registration order (= the order backward completes them: the two 65536-wide last layers, 45 % of all gradient bytes,
+    first), a post-accumulate-grad hook counts completed gradients per bucket and, when a bucket is full, forks a side
+    stream that flattens the bucket, AVG-all-reduces it over NCCL and scatters it back while the main stream continues
+    with the remaining backward kernels.  finish() launches whatever is left and joins the side stream before the
+    optimiser sweep.  The result is independent of the bucketing (same AVG per element)."""
+
+    def __init__(self, params, bucket_bytes: int = 48 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self.count = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+        self.side = torch.cuda.Stream()
+        self.enabled = True
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def _hook(self, p) -> None:
+        if not self.enabled:
+            return
+        bi = self.bucket_of[id(p)]
+        self.count[bi] += 1
+        if self.count[bi] == len(self.buckets[bi]) and not self.launched[bi]:
+            self._launch(bi)
+
+    def _launch(self, bi: int) -> None:
+        self.launched[bi] = True
+        grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
+        if not grads:
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+    def finish(self) -> None:
+        for bi in range(len(self.buckets)):
+            if not self.launched[bi]:
+                self._launch(bi)
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.count = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+
+
 class SelfDistillStep:
     """One training step.  optimizer: a torch optimizer (the reference's own sequence: clip kernel, cancel grads,
     optimizer.step(), EMA kernel) or an esvit_b200.optim.FusedAdamWEMA (clip + AdamW + EMA in one sweep).
@@ -73,6 +129,9 @@ class SelfDistillStep:
         self._warm = 0
         for p in self.teacher.parameters():
             p.requires_grad = False
+        self._reducer = None
+        if self.grad_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._reducer = _GradReducer(list(self.student.parameters()))
 
     # ---- the step body (eager; also what gets captured) ---------------------------------------------------
     def _body(self, images: List[torch.Tensor], epoch: int) -> torch.Tensor:
@@ -100,13 +159,11 @@ class SelfDistillStep:
         return loss.detach()
 
     def reduce_gradients(self) -> None:
-        """DDP's gradient AVG all-reduce (main_esvit.py:377) for the graph-captured step: no-op at world size 1."""
-        if not (self.grad_allreduce and dist.is_initialized() and dist.get_world_size() > 1):
-            return
-        grads = [p.grad for p in self.student.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])  # one bandwidth-bound message (295 MB for Swin-T)
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        """DDP's gradient AVG all-reduce (main_esvit.py:377) for the graph-captured step: buckets whose gradients were
+        complete during backward have already been launched on the side stream by the post-accumulate hooks
+        (_GradReducer); this launches the rest and joins the side stream.  No-op at world size 1."""
+        if self._reducer is not None:
+            self._reducer.finish()
 
     def __call__(self, images: Sequence[torch.Tensor], epoch: int, lr: float, wd: float, momentum: float) -> torch.Tensor:
         images = list(images)

@@ -728,11 +728,12 @@ class WeightNormFn(Function):
     @once_differentiable
     def backward(ctx, gw):
         v, g, norm = ctx.saved_tensors
-        gw = _chk(gw, BF16, "gw")
+        f32 = gw.dtype == F32  # fp32 from esvit_gemm_wgrad, bf16 from a library GEMM
+        gw = _chk(gw, F32 if f32 else BF16, "gw")
         K, Dm = v.shape
         dv = torch.empty_like(v)
         dg = torch.empty_like(g) if ctx.needs_input_grad[1] else None
-        _lib.call("esvit_weight_norm_bwd", _p(v), _p(g), _p(norm), _p(gw), _p(dv), _p(dg), K, Dm, _stream())
+        _lib.call("esvit_weight_norm_bwd", _p(v), _p(g), _p(norm), _p(gw), 1 if f32 else 0, _p(dv), _p(dg), K, Dm, _stream())
         return dv, dg
 
 

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops, shadow
+from . import linear, ops, shadow
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -37,6 +37,9 @@ USE_TCGEN05_FC1 = os.environ.get("ESVIT_TCGEN05_FC1", "1") != "0"
 # forward instead of once per group; attention / patch merging / pooling launch per group on slices of the same buffers
 # (SwinTransformer._forward_fused_groups).  ESVIT_FUSE_GROUPS=0 restores the reference's per-group loop.
 USE_FUSED_GROUPS = os.environ.get("ESVIT_FUSE_GROUPS", "1") != "0"
+# every Linear (forward, input gradient, weight gradient) on the second-generation tcgen05 GEMM family (esvit_b200.linear)
+# instead of library GEMMs; ESVIT_GEMM2=0 restores the library-GEMM path of round 1
+USE_GEMM2 = os.environ.get("ESVIT_GEMM2", "0") != "0"
 
 
 def _trunc_normal_(t: Tensor, std: float = .02) -> Tensor:
@@ -103,6 +106,9 @@ class _CastCache:
 def _lin_c(x: Tensor, lin: nn.Linear, cc: Optional[_CastCache]) -> Tensor:
     """bf16 library GEMM x @ W^T + b (bias in the GEMM epilogue).  The bias GRADIENT is not computed here: the consumer
     kernel (window attention / GELU / residual add + LN backward) column-sums it, see ops.LinearBiasFn."""
+    if USE_GEMM2:
+        w16 = shadow.as_bf16(lin.weight, track_grad=False) if cc is None else cc.nograd(lin.weight)
+        return linear.LinearFn.apply(x, lin.weight, w16, lin.bias)
     w = shadow.as_bf16(lin.weight) if cc is None else cc(lin.weight)
     if lin.bias is None:
         with torch.autocast("cuda", enabled=False):
@@ -144,6 +150,10 @@ class Mlp(nn.Module):
     def fused(self, x: Tensor, cc: Optional[_CastCache] = None) -> Tensor:
         """x bf16 [..., C] -> fc2(gelu(fc1(x))) bf16.  fc1.bias gets its gradient from the GELU backward kernel; the
         caller must route fc2.bias through the residual-add kernel (ops.add_layer_norm / residual_add delta_bias)."""
+        if USE_GEMM2 and self.fc2.bias is not None:
+            cc = cc if cc is not None else _CastCache()
+            return linear.MlpFn.apply(x, self.fc1.weight, cc.nograd(self.fc1.weight), self.fc1.bias, self.fc2.weight,
+                                      cc.nograd(self.fc2.weight), self.fc2.bias)
         if USE_TCGEN05_FC1:
             w1 = shadow.as_bf16(self.fc1.weight) if cc is None else cc(self.fc1.weight)
             if torch.is_grad_enabled() and self.fc1.weight.requires_grad and self.fc2.bias is not None:

@@ -12,7 +12,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops, shadow
+from . import linear, ops, shadow
+from .swin_transformer import USE_GEMM2
 
 BF16 = torch.bfloat16
 
@@ -31,6 +32,8 @@ class _WeightNormLinear(nn.Module):
         return ops.WeightNormFn.apply(self.weight_v, self.weight_g)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if USE_GEMM2:
+            return linear.LastLayerFn.apply(x, self.effective_weight())
         with torch.autocast("cuda", enabled=False):
             return F.linear(x, self.effective_weight())
 
@@ -65,6 +68,13 @@ class DINOHead(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x.to(BF16)
         mods = [self.mlp] if isinstance(self.mlp, nn.Linear) else list(self.mlp)
+        lins = [m for m in mods if isinstance(m, nn.Linear)]
+        if USE_GEMM2 and len(lins) == 3 and len(mods) == 5:
+            args = []
+            for m in lins:
+                args += [m.weight, shadow.as_bf16(m.weight, track_grad=False), m.bias]
+            x = linear.HeadMlpFn.apply(x, *args)
+            return self.last_layer(ops.L2NormFn.apply(x, 1e-12))
         with torch.autocast("cuda", enabled=False):
             for i, m in enumerate(mods):
                 if not isinstance(m, nn.Linear):

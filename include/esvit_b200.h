@@ -124,8 +124,9 @@ int esvit_mul_bwd_dbias(const void* gp, const void* dy, void* dx, float* dbias, 
 int esvit_l2norm_fwd(const void* x, void* y, float* inv, float eps, long long R, int D, void* stream);
 int esvit_l2norm_bwd(const void* x, const void* dy, const float* inv, void* dx, long long R, int D, void* stream);
 int esvit_weight_norm_fwd(const float* v, const float* g, void* w, float* norm, long long K, int D, void* stream);
-int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, const void* dw, float* dv, float* dg,
-                          long long K, int D, void* stream);
+/* dw: bf16 [K,D], or fp32 when dw_is_f32 (the fp32 weight gradient of esvit_gemm_wgrad) */
+int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, const void* dw, int dw_is_f32, float* dv,
+                          float* dg, long long K, int D, void* stream);
 
 /* ---- DINOLoss / DDINOLoss ---------------------------------------------------- main_esvit.py:620-648, :683-750
  * row_lse: lse[r] = log sum_k exp((x[r,k] - center[k]) * inv_temp)   (center NULL for student rows).

@@ -16,3 +16,10 @@ timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2b_bench.json 2>
 echo "bench rc=$?"
 tail -c 2500 gpurun_out/r2b_bench.json
 tail -5 gpurun_out/r2b_bench.err
+# the same model-level parity tests and the bench with every Linear on the second-generation GEMM family
+ESVIT_GEMM2=1 timeout 900 python -m pytest tests/test_model_gpu.py tests/test_real_shapes_gpu.py -q -m gpu > gpurun_out/r2b_pytest_gemm2.log 2>&1
+echo "pytest GEMM2 rc=$?"; tail -15 gpurun_out/r2b_pytest_gemm2.log
+ESVIT_GEMM2=1 timeout 600 python bench.py --steps 20 --warmup 3 --no-gpu-reference --no-cpu-baseline --profile gpurun_out/r2b_prof_gemm2.txt > gpurun_out/r2b_bench_gemm2.json 2> gpurun_out/r2b_bench_gemm2.err
+echo "bench GEMM2 rc=$?"
+tail -c 1500 gpurun_out/r2b_bench_gemm2.json
+tail -5 gpurun_out/r2b_bench_gemm2.err
