@@ -15,7 +15,9 @@
 //   * epilogues (template EPI): bias -> bf16 | bias + exact GELU (+ gelu' for the backward) | accumulator * TMA-loaded
 //     multiplier + column sums (fc2 dgrad fused with GELU' and the fc1 bias gradient) | fp32 split-K partials for the
 //     weight gradients (deterministic: partial tiles + fold kernel, no atomics).
-//   * 16 epilogue warps work in 128-column chunks: tcgen05.ld -> math -> 128B-swizzled smem slabs -> TMA stores.
+//   * 16 epilogue warps = FOUR INDEPENDENT quads; a quad owns one 128-row x 64-column slab at a time (tcgen05.ld -> math ->
+//     128B-swizzled smem slab -> its own TMA store stream, its own named barrier), slabs are dealt round-robin over the
+//     quads, so four slabs of up to two tiles are in flight per SM and no barrier ever spans more than 128 threads.
 // Persistent: one CTA per SM, static round-robin over (split, m tile, n tile) work items.
 #include <cuda.h>
 
@@ -54,38 +56,45 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// bounded spin: a mis-programmed pipeline traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// bounded spin: a mis-programmed pipeline traps after ~2 s of wall time instead of hanging the GPU
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 27); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    if constexpr (CLUSTER) {  // acquire at cluster scope: completed by the peer CTA / the async proxy of the pair
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(a), "r"(parity)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(a), "r"(parity)
+          : "memory");
+    }
     if (done) return;
+    if ((it & 1023u) == 1023u) {
+      const uint64_t t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
   }
-  __trap();
 }
-// acquire at cluster scope: the barrier was completed by the peer CTA / the async proxy of the pair
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 27); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_impl<false>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait_impl<true>(bar, parity); }
 template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1) {
   if constexpr (CG == 2) {  // both CTAs of the pair issue their own loads; completion bytes go to the LEADER's barrier
@@ -105,7 +114,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
+// named barrier of one epilogue quad (4 warps): ids 1..4
+__device__ __forceinline__ void quad_bar(int g) { asm volatile("bar.sync %0, 128;\n" ::"r"(g + 1) : "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -188,26 +198,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// exact-erf GELU without MUFU.RCP: Phi(x) = 0.5 + u * P(u^2), u = clamp(x, -4, 4) / 4, P an odd-power minimax fit of
-// degree 15 (|Phi error| < 5e-5, |gelu error| < 3e-4 over all x: below bf16 output resolution); gelu'(x) =
-// Phi(x) + x * phi(x) needs one ex2.  (elementwise.cu keeps the A&S 7.1.26 form for the un-fused kernels.)
-constexpr float PHI_C1 = 1.595331648e+00f, PHI_C3 = -4.233035160e+00f, PHI_C5 = 9.873116463e+00f, PHI_C7 = -1.706059038e+01f,
-                PHI_C9 = 2.086927719e+01f, PHI_C11 = -1.683686549e+01f, PHI_C13 = 7.925319928e+00f, PHI_C15 = -1.632603070e+00f;
-__device__ __forceinline__ float gelu_cdf(float x) {
-  const float u = fminf(fmaxf(x, -4.f), 4.f) * 0.25f;
-  const float u2 = u * u;
-  float p = PHI_C15;
-  p = fmaf(p, u2, PHI_C13);
-  p = fmaf(p, u2, PHI_C11);
-  p = fmaf(p, u2, PHI_C9);
-  p = fmaf(p, u2, PHI_C7);
-  p = fmaf(p, u2, PHI_C5);
-  p = fmaf(p, u2, PHI_C3);
-  p = fmaf(p, u2, PHI_C1);
-  return fmaf(u, p, 0.5f);
+// GELU in the epilogue: Phi(x) = 0.5 + 0.5 tanh(x (a + b x^2)) with ONE MUFU (tanh.approx) and 5 FMA-pipe instructions;
+// |gelu - x Phi_erf(x)| < 1e-3 absolute at |x| ~ 4 and < 3e-4 for |x| < 3 - below the bf16 resolution of the stored value
+// (0.4 % relative).  The stored derivative is the derivative of THIS function (0 MUFU, 5 more instructions), so forward
+// and backward are consistent.  The epilogue is instruction-bound, not HBM-bound: the erf form (2 MUFU + 14 ALU) and a
+// degree-15 minimax polynomial (19 ALU) both measured slower than the HBM write stream they feed.
+constexpr float GELU_A = 0.7978845608028654f, GELU_B = 0.7978845608028654f * 0.044715f;
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float gelu_pdf_x(float x) {  // x * phi(x) = x * exp(-x^2/2) / sqrt(2 pi)
-  return x * 0.3989422804014327f * exp2f(-0.72134752044448170f * x * x);
+__device__ __forceinline__ void gelu_fwd(float x, float& y) {
+  const float x2 = x * x;
+  const float th = tanh_approx(x * fmaf(GELU_B, x2, GELU_A));
+  const float hx = 0.5f * x;
+  y = fmaf(hx, th, hx);
+}
+__device__ __forceinline__ void gelu_fwd_grad(float x, float& y, float& dy) {
+  const float x2 = x * x;
+  const float th = tanh_approx(x * fmaf(GELU_B, x2, GELU_A));
+  const float hx = 0.5f * x;
+  y = fmaf(hx, th, hx);
+  // d/dx [0.5 x (1 + th)] = 0.5 (1 + th) + 0.5 x (1 - th^2) (a + 3 b x^2)
+  const float sech2 = fmaf(-th, th, 1.f);
+  dy = fmaf(hx * sech2, fmaf(3.f * GELU_B, x2, GELU_A), fmaf(0.5f, th, 0.5f));
 }
 
 struct Params {
@@ -226,14 +241,16 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;                       // rows (K-major) / MN elements (MN-major) of B staged per CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLABS_PER_CHUNK = (EPI == EPI_GELU || EPI == EPI_MUL) ? 4 : 2;  // out (+ pre / multiplier) x 2 halves
-  static constexpr int NSLAB = (EPI == EPI_F32) ? 0 : 2 * SLABS_PER_CHUNK;              // double-buffered over chunks
+  static constexpr int SPT = BN / 64;                          // 64-column slabs per tile
+  static constexpr int SPG = (EPI == EPI_GELU || EPI == EPI_MUL) ? 2 : 1;  // staging slabs per quad: out (+ gelu' / multiplier)
+  static constexpr int NSLAB = (EPI == EPI_F32) ? 0 : 4 * SPG;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int AVAIL = SMEM_LIMIT - 1024 /*alignment slack*/ - BAR_BYTES - NSLAB * SLAB_BYTES;
   static constexpr int STAGES_RAW = AVAIL / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + NSLAB * SLAB_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 256 / 512)
+  static constexpr int QUADS_PER_TILE = SPT < 4 ? SPT : 4;     // quads that read one accumulator
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
@@ -253,9 +270,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]  (the leader's copy is the one in use)
-  uint64_t* mult_full = tmem_empty + 2;   // [2]  EPI_MUL: multiplier chunk landed in its slabs
-  uint64_t* mult_empty = mult_full + 2;   // [2]  ... and has been consumed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mult_empty + 2);
+  uint64_t* mult_full = tmem_empty + 2;   // [4]  EPI_MUL: a quad's multiplier slab has landed
+  uint64_t* mult_empty = mult_full + 4;   // [4]  ... and has been consumed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mult_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -270,8 +287,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * NUM_EPI_WARPS); }
-    for (int i = 0; i < 2; i++) { mbar_init(&mult_full[i], 1); mbar_init(&mult_empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * 4 * C::QUADS_PER_TILE); }
+    for (int i = 0; i < 4; i++) { mbar_init(&mult_full[i], 1); mbar_init(&mult_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 2) {  // one warp (the same warp index in both CTAs of a pair) allocates TMEM and frees it at the end
@@ -331,21 +348,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     // straight into the slabs the epilogue reads it from.
     if constexpr (EPI == EPI_MUL) {
       if (elect_one()) {
-        int chunk_ctr = 0;
-        for (int item = cluster_id; item < num_items; item += num_clusters) {
+        int uses[4] = {0, 0, 0, 0};  // slabs loaded so far for each quad
+        int local = 0;
+        for (int item = cluster_id; item < num_items; item += num_clusters, local++) {
           const int tile = item % tiles_mn;
           const int m0 = (tile / n_tiles) * (BM * CG) + (int)rank * BM, n0 = (tile % n_tiles) * BN;
-          for (int c = 0; c < BN / 128; c++) {
-            const int nc = n0 + c * 128;
-            if (nc >= p.N) break;
-            const int slot = chunk_ctr & 1;
-            mbar_wait(&mult_empty[slot], ((chunk_ctr >> 1) & 1) ^ 1);
-            uint8_t* sm = slabs + (slot * 4 + 2) * SLAB_BYTES;
-            const bool two = nc + 64 < p.N;
-            mbar_expect_tx(&mult_full[slot], two ? 2 * SLAB_BYTES : SLAB_BYTES);
-            tma_load_2d<1>(smem_u32(sm), &map_pre, smem_u32(&mult_full[slot]), nc, m0);
-            if (two) tma_load_2d<1>(smem_u32(sm + SLAB_BYTES), &map_pre, smem_u32(&mult_full[slot]), nc + 64, m0);
-            chunk_ctr++;
+#pragma unroll
+          for (int sl = 0; sl < C::SPT; sl++) {
+            const int ns = n0 + sl * 64;
+            if (ns >= p.N) break;
+            const int g = (local * C::SPT + sl) & 3;  // the quad this slab is dealt to
+            mbar_wait(&mult_empty[g], ((uses[g] & 1) ^ 1));
+            mbar_expect_tx(&mult_full[g], SLAB_BYTES);
+            tma_load_2d<1>(smem_u32(slabs + (g * 2 + 1) * SLAB_BYTES), &map_pre, smem_u32(&mult_full[g]), ns, m0);
+            uses[g]++;
           }
         }
       }
@@ -384,125 +400,132 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       }
     }
   } else {
-    // ===================== epilogue warps: TMEM -> registers -> math -> swizzled smem slabs -> TMA store ==========
+    // ===================== epilogue: four independent warp quads; TMEM -> registers -> math -> smem slab -> TMA store ======
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int colq = (warp - 2) >> 2;          // 32-column slice of the 128-column chunk handled by this warp
+    const int g = (warp - 2) >> 2;             // quad
     const int r = q * 32 + lane;               // row of the tile owned by this thread
-    int local = 0, chunk_ctr = 0;
+    const bool lead = ((warp - 2) & 3) == 0 && lane == 0;      // first thread of the quad: owns its TMA store stream
+    uint8_t* s_out = slabs + g * C::SPG * SLAB_BYTES;          // this quad's staging slab(s)
+    uint8_t* s_aux = s_out + SLAB_BYTES;                       // gelu' out / multiplier in (SPG == 2)
+    int local = 0, uses = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, local++) {
       const int tile = item % tiles_mn, split = item / tiles_mn;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       const int m0 = (tile / n_tiles) * (BM * CG) + (int)rank * BM, n0 = (tile % n_tiles) * BN;
-      mbar_wait_cluster(&tmem_full[as], aphase);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      bool waited = false;
 #pragma unroll 1
-      for (int c = 0; c < BN / 128; c++) {
-        const int nc = n0 + c * 128;
-        const bool last = (c == BN / 128 - 1) || (nc + 128 >= p.N);
-        if (nc < p.N) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 128 + colq * 32), v);
-          if (last) {  // accumulator drained into registers: the MMA warp may start the next-but-one tile
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
-          }
-          if constexpr (EPI == EPI_F32) {
-            // split-K partial: fp32 tile straight to the workspace (each thread: 32 consecutive floats of its row)
-            const int row = m0 + r, col0 = nc + colq * 32;
-            if (row < p.M) {
-              float* dst = p.part + ((long long)split * p.M + row) * p.N + col0;
+      for (int sl = 0; sl < C::SPT; sl++) {
+        if (((local * C::SPT + sl) & 3) != g) continue;  // slabs are dealt round-robin over the quads
+        const int ns = n0 + sl * 64;
+        const bool exists = ns < p.N;
+        if (!waited) {
+          mbar_wait_cluster(&tmem_full[as], aphase);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          waited = true;
+        }
+        if (exists && EPI != EPI_F32) {
+          // this quad's previous TMA store must have finished READING the slab before it is overwritten
+          if (lead) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          quad_bar(g);
+          if constexpr (EPI == EPI_MUL) mbar_wait(&mult_full[g], uses & 1);
+        }
+        if (exists) {
 #pragma unroll
-              for (int j = 0; j < 8; j++)
-                if (col0 + j * 4 < p.N)
-                  *reinterpret_cast<float4*>(dst + j * 4) = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
-                                                                         __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
-            }
-          } else {
-            const int slot = chunk_ctr & 1;
-            uint8_t* s_out = slabs + slot * C::SLABS_PER_CHUNK * SLAB_BYTES;          // 2 slabs: columns [0,64) [64,128)
-            uint8_t* s_aux = s_out + 2 * SLAB_BYTES;                                  // gelu' out / multiplier in
-            uint8_t* so = s_out + (colq >> 1) * SLAB_BYTES + r * 128;
-            uint8_t* sp = s_aux + (colq >> 1) * SLAB_BYTES + r * 128;
-            // the TMA stores issued two chunks ago (same slabs) must have finished READING them
-            if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-            epi_bar();
-            if constexpr (EPI == EPI_MUL) {
-              // out = acc * mult (fc2 input-gradient GEMM fused with the GELU backward: mult = gelu'(pre-activation))
-              mbar_wait(&mult_full[slot], (chunk_ctr >> 1) & 1);
+          for (int hh = 0; hh < 2; hh++) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + sl * 64 + hh * 32), v);
+            const int c0 = ns + hh * 32;
+            if constexpr (EPI == EPI_F32) {
+              // split-K partial: fp32 straight to the workspace (each thread: 32 consecutive floats of its row)
+              const int row = m0 + r;
+              if (row < p.M) {
+                float* dst = p.part + ((long long)split * p.M + row) * p.N + c0;
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const int sw = (((colq & 1) * 4 + j) ^ (r & 7)) * 16;
-                float fm[8], g[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(sp + sw), fm);
-#pragma unroll
-                for (int t = 0; t < 8; t++) g[t] = __uint_as_float(v[j * 8 + t]) * fm[t];
-                *reinterpret_cast<bf16x8*>(so + sw) = pack8(g);
+                for (int j = 0; j < 8; j++)
+                  if (c0 + j * 4 < p.N)
+                    *reinterpret_cast<float4*>(dst + j * 4) = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
+                                                                           __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
               }
             } else {
-              const bool store_pre = (EPI == EPI_GELU) && p.has_pre;
+              uint8_t* so = s_out + r * 128;
+              uint8_t* sp = s_aux + r * 128;
 #pragma unroll
               for (int j = 0; j < 4; j++) {  // 4 chunks of 8 columns = 16 B
-                const int cbase = nc + colq * 32 + j * 8;
-                float f[8], g[8];
+                const int cb = c0 + j * 8;
+                const int sw = ((hh * 4 + j) ^ (r & 7)) * 16;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+                float gq[8];
+                if constexpr (EPI == EPI_MUL) {
+                  float fm[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(sp + sw), fm);
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                  const float x = __uint_as_float(v[j * 8 + t]) + ((p.bias && cbase + t < p.N) ? __ldg(p.bias + cbase + t) : 0.f);
-                  if constexpr (EPI == EPI_GELU) {
-                    const float cdf = gelu_cdf(x);
-                    g[t] = x * cdf;
-                    f[t] = store_pre ? cdf + gelu_pdf_x(x) : 0.f;
-                  } else {
-                    g[t] = x;
+                  for (int t = 0; t < 8; t++) gq[t] = __uint_as_float(v[j * 8 + t]) * fm[t];
+                  *reinterpret_cast<bf16x8*>(so + sw) = pack8(gq);
+                } else {
+                  float b8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  if (p.bias && cb < p.N) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
+                    b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
                   }
-                }
-                const int sw = (((colq & 1) * 4 + j) ^ (r & 7)) * 16;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-                *reinterpret_cast<bf16x8*>(so + sw) = pack8(g);
-                if constexpr (EPI == EPI_GELU) { if (store_pre) *reinterpret_cast<bf16x8*>(sp + sw) = pack8(f); }
-              }
-            }
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy smem writes -> visible to TMA
-            epi_bar();
-            if (threadIdx.x == 64) {
-              if constexpr (EPI == EPI_MUL) mbar_arrive(&mult_empty[slot]);  // every epilogue thread is past its multiplier reads
-              tma_store_2d(&map_out, s_out, nc, m0);
-              if (nc + 64 < p.N) tma_store_2d(&map_out, s_out + SLAB_BYTES, nc + 64, m0);
-              if constexpr (EPI == EPI_GELU) {
-                if (p.has_pre) {
-                  tma_store_2d(&map_pre, s_aux, nc, m0);
-                  if (nc + 64 < p.N) tma_store_2d(&map_pre, s_aux + SLAB_BYTES, nc + 64, m0);
-                }
-              }
-              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-            }
-            if constexpr (EPI == EPI_MUL) {
-              // column sums over the staged bf16 chunk: thread = (column pair, 16-row group); rows >= M hold zeros.
-              // Into this CTA's PRIVATE row: all CTAs adding into one [N] vector serialise in the L2 atomic units.
-              const int te = threadIdx.x - 64, cp = te & 63, rg = te >> 6;
-              const uint8_t* base = s_out + (cp >> 5) * SLAB_BYTES + (cp & 3) * 4;
-              const int chunk16 = (cp & 31) >> 2;
-              float s0 = 0.f, s1 = 0.f;
+                  if constexpr (EPI == EPI_GELU) {
+                    if (p.has_pre) {
+                      float fq[8];
 #pragma unroll
-              for (int i = 0; i < 16; i++) {
-                const int row = rg * 16 + i;
-                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((chunk16 ^ (row & 7)) * 16));
-                s0 += __uint_as_float(w2 << 16);
-                s1 += __uint_as_float(w2 & 0xffff0000u);
+                      for (int t = 0; t < 8; t++) gelu_fwd_grad(__uint_as_float(v[j * 8 + t]) + b8[t], gq[t], fq[t]);
+                      *reinterpret_cast<bf16x8*>(sp + sw) = pack8(fq);
+                    } else {
+#pragma unroll
+                      for (int t = 0; t < 8; t++) gelu_fwd(__uint_as_float(v[j * 8 + t]) + b8[t], gq[t]);
+                    }
+                  } else {
+#pragma unroll
+                    for (int t = 0; t < 8; t++) gq[t] = __uint_as_float(v[j * 8 + t]) + b8[t];
+                  }
+                  *reinterpret_cast<bf16x8*>(so + sw) = pack8(gq);
+                }
               }
-              float* dst = p.colsum + (long long)blockIdx.x * p.N;
-              const int col = nc + cp * 2;
-              if (col < p.N) atomicAdd(dst + col, s0);
-              if (col + 1 < p.N) atomicAdd(dst + col + 1, s1);
             }
-            chunk_ctr++;
           }
         }
-        if (last) break;
+        // this warp is done with the accumulator: the MMA warp may start the next-but-one tile once every reader arrived
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
+        if (exists && EPI != EPI_F32) {
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy smem writes -> visible to TMA
+          quad_bar(g);
+          if (lead) {
+            if constexpr (EPI == EPI_MUL) mbar_arrive(&mult_empty[g]);  // every thread of the quad is past its multiplier reads
+            tma_store_2d(&map_out, s_out, ns, m0);
+            if constexpr (EPI == EPI_GELU) { if (p.has_pre) tma_store_2d(&map_pre, s_aux, ns, m0); }
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          }
+          if constexpr (EPI == EPI_MUL) {
+            // column sums over the staged bf16 slab: thread = (column pair, 32-row group); rows >= M hold zeros.
+            // Into this CTA's PRIVATE row: all CTAs adding into one [N] vector serialise in the L2 atomic units.
+            const int te = threadIdx.x - 64 - g * 128, cp = te & 31, rg = te >> 5;
+            const uint8_t* base = s_out + (cp & 3) * 4;
+            const int chunk16 = cp >> 2;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const int row = rg * 32 + i;
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((chunk16 ^ (row & 7)) * 16));
+              s0 += __uint_as_float(w2 << 16);
+              s1 += __uint_as_float(w2 & 0xffff0000u);
+            }
+            float* dst = p.colsum + (long long)blockIdx.x * p.N;
+            const int col = ns + cp * 2;
+            if (col < p.N) atomicAdd(dst + col, s0);
+            if (col + 1 < p.N) atomicAdd(dst + col + 1, s1);
+          }
+          uses++;
+        }
       }
     }
     if constexpr (EPI != EPI_F32) {
-      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // stores complete before exit
+      if (lead) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // stores complete before exit
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -640,8 +663,9 @@ static int launch(const Call& c, int epi, int cg, int bn, void* stream, int* gri
   return ESVIT_ERR_BAD_ARG;
 }
 
-// tile shape policy (overridable per call through `tile` = cg * 1000 + bn, 0 = automatic)
+// tile shape policy (overridable per call through `tile` = forced_splits * 10000 + cg * 1000 + bn, 0 = automatic)
 static void pick_tile(long long M, int N, int tile, int* cg, int* bn) {
+  tile %= 10000;
   if (tile > 0) { *cg = tile / 1000; *bn = tile % 1000; return; }
   *bn = N > 128 ? 256 : 128;
   *cg = M > 128 ? 2 : 1;
@@ -713,7 +737,10 @@ ESVIT_API int esvit_gemm_wgrad(const void* dy, const void* x, float* dw, float* 
   const int tiles = m_tiles * n_tiles;
   const int k_blocks = (int)((T + tg2::BK - 1) / tg2::BK);
   const int clusters = (esvit_num_sms() > tg2::MAX_GRID ? tg2::MAX_GRID : esvit_num_sms()) / cg;
-  int splits = (2 * clusters + tiles - 1) / tiles;            // ~2 work items per cluster
+  // one wave of work items: every cluster gets (at most) one K-slice of one output tile, slices of >= 8 K blocks
+  int splits = tiles >= clusters ? 1 : clusters / tiles;
+  if (splits > k_blocks / 8) splits = k_blocks / 8;
+  if (tile >= 10000) splits = tile / 10000;                   // forced (tests / tuning)
   const long long cap = wgrad_ws_floats(N, K) / ((long long)N * K);
   if (splits > cap) splits = (int)cap;
   if (splits > k_blocks) splits = k_blocks;

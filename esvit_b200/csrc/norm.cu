@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
 
 // backward: G = dxo + LNbwd(dy) ; dx = G ; ddelta = keep * G ; dgamma += dy*xhat ; dbeta += dy ; ddbias += keep*G
 template <int LPR, int NV, typename DyT>
-__global__ void __launch_bounds__(NV <= 4 ? 256 : 128) add_ln_bwd_kernel(
+// NV <= 3 (C <= 384 at 8/16/32 lanes per row: every stage-0..2 launch, 85 % of this kernel's bytes): 3 CTAs/SM at 80
+// registers (32 bytes of spill) instead of 2 at 128 - the kernel is latency-bound on bytes in flight, not on ALU
+__global__ void __launch_bounds__(NV <= 4 ? 256 : 128, NV <= 3 ? 3 : 1) add_ln_bwd_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ dxo, const float* __restrict__ xs,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
     const float* __restrict__ keep, int tokens_per_sample, float* __restrict__ dx, bf16* __restrict__ ddelta,
@@ -420,7 +422,8 @@ ESVIT_API int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo,
   const int threads = nv <= 4 ? 256 : 128;
   const long long warp_rows = (T + 32 / lpr - 1) / (32 / lpr);
   // every CTA ends with 3*C global atomics: keep the CTA count modest
-  const int grid = row_grid(warp_rows, threads / 32, threads == 256 ? 4 : 8);
+  // persistent grid = resident CTAs x small integer (no partial last wave)
+  const int grid = row_grid(warp_rows, threads / 32, nv <= 3 ? 3 : (threads == 256 ? 4 : 8));
   const size_t smem = 3 * (size_t)C * sizeof(float);
   bool done = false;
 #define X(L, N)                                                                                                      \

@@ -73,7 +73,7 @@ class MlpFn(Function):
 
     @staticmethod
     def forward(ctx, x, w1p, w1, b1, w2p, w2, b2):
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        need = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward: needs_input_grad is the signal)
         if need:
             h, pre = ops.gemm(x, w1, b1, act=1, want_pre=True)
         else:
@@ -107,7 +107,7 @@ class HeadMlpFn(Function):
 
     @staticmethod
     def forward(ctx, x, w1p, w1, b1, w2p, w2, b2, w3p, w3, b3):
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        need = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward: needs_input_grad is the signal)
         if need:
             h1, p1 = ops.gemm(x, w1, b1, act=1, want_pre=True)
             h2, p2 = ops.gemm(h1, w2, b2, act=1, want_pre=True)

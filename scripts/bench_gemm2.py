@@ -79,6 +79,9 @@ def main():
             x = (torch.randn(M, K, device=d) * 0.5).to(BF16)
             lib = timeit(lambda: (dy.t() @ x).float())
             mine = {t: timeit(lambda: ops.gemm_wgrad(dy, x, tile=t)) for t in TILES}
+            if M <= 50000:  # forced split counts (tile + 10000 * splits): where does the time go for the short-K shapes?
+                for sp in (1, 2, 4, 8):
+                    mine[f"2256/s{sp}"] = timeit(lambda: ops.gemm_wgrad(dy, x, tile=2256 + 10000 * sp))
         line(kind, M, N, K, lib, mine)
         del mine
         torch.cuda.empty_cache()
