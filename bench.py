@@ -249,6 +249,8 @@ def run_reference(args):
     if rank != 0:
         return
     device = args.device or "cpu"
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     if device == "cpu":
         steps, warmup = min(steps, 3), min(warmup, 1)  # bounded sample: ~1-8 s per B=2 step depending on the host
@@ -298,10 +300,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs CUDA (there is no CPU fallback of the product path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
@@ -325,8 +327,10 @@ def main():
     # ---- roofline of the dominant kernel: CUDA events around each launch, in EAGER steps (events cannot be
     # recorded inside a replayed graph); these steps double as the warm-up the graph capture needs -------------
     _lib.reset_counters()
-    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_window_attn_bwd", "esvit_window_attn_fwd", "esvit_gemm_bias_act",
-                            "esvit_gemm_mul_colsum"])
+    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_dino_ce_fwd", "esvit_window_attn_bwd", "esvit_window_attn_fwd",
+                            "esvit_gemm_bias_act", "esvit_gemm_mul_colsum", "esvit_gemm_bf16", "esvit_gemm_mul_colsum2",
+                            "esvit_gemm_wgrad", "esvit_add_ln_fwd", "esvit_add_ln_bwd", "esvit_patch_embed_fwd",
+                            "esvit_patch_embed_bwd"])
     n_eager = 3 if args.min_warmup >= 3 else 1
     for _ in range(n_eager):
         l = one_step(crops)
@@ -447,10 +451,59 @@ def main():
                        (r_gemm, "gemm_bias_act"), (r_gemm2, "gemm_mul_colsum")):
             if r and key in traffic:
                 r["traffic"] = traffic[key]
-        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm, r_gemm2) if r]
+        # second-generation GEMM family (every Linear): bytes = operands read + result written; flops = 2 M N K
+        def gemm_bytes(t):
+            out_b = 2 * t["M"] * t["N"] * (2 if t.get("pre") else 1)
+            return 2 * (t["M"] * t["K"] + t["N"] * t["K"]) + out_b
+        bf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+
+        def with_flops(r, name, flops_fn, extra=None):
+            if r:
+                sel = [t for t in timed if t["name"] == name and (extra is None or extra(t))]
+                fl = sum(flops_fn(t) for t in sel)
+                ms_ = sum(t["ms"] for t in sel)
+                r["tflops"] = fl / (ms_ / 1e3) / 1e12
+                r["tensor_frac_of_sustained_bf16"] = r["tflops"] / bf_peak
+            return r
+        g_fwd = with_flops(agg("esvit_gemm_bf16", gemm_bytes, "tg2::gemm_kernel forward Linear (+bias / +GELU) (all launches of a step)",
+                               extra=lambda t: not t["b_mn"]),
+                           "esvit_gemm_bf16", lambda t: 2.0 * t["M"] * t["N"] * t["K"], lambda t: not t["b_mn"])
+        g_dgr = with_flops(agg("esvit_gemm_bf16", gemm_bytes, "tg2::gemm_kernel input gradient (MN-major B) (all launches of a step)",
+                               extra=lambda t: t["b_mn"]),
+                           "esvit_gemm_bf16", lambda t: 2.0 * t["M"] * t["N"] * t["K"], lambda t: t["b_mn"])
+        g_mul = with_flops(agg("esvit_gemm_mul_colsum2", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
+                               "tg2::gemm_kernel fc2-dgrad * gelu' + colsum (all launches of a step)"),
+                           "esvit_gemm_mul_colsum2", lambda t: 2.0 * t["M"] * t["N"] * t["K"])
+        g_wgr = with_flops(agg("esvit_gemm_wgrad", lambda t: 2 * t["T"] * (t["N"] + t["K"]) + 4 * t["N"] * t["K"],
+                               "tg2::gemm_kernel weight gradient (MN-major A and B, split-K) + fold (all launches of a step)"),
+                           "esvit_gemm_wgrad", lambda t: 2.0 * t["T"] * t["N"] * t["K"])
+        r_lnf = agg("esvit_add_ln_fwd", lambda t: t["T"] * t["C"] * ((4 if t["has_x"] else 0) + (2 if t["has_delta"] else 0) + 4 + 2),
+                    "add_ln_fwd_kernel (all launches of a step)")
+        r_lnb = agg("esvit_add_ln_bwd", lambda t: 16 * t["T"] * t["C"], "add_ln_bwd_kernel (all launches of a step)")
+        r_cef = agg("esvit_dino_ce_fwd", lambda t: (rows_s + rows_t) * t["K"] * 2, "dino_ce_fwd_kernel (region rows)",
+                    extra=lambda t: t["rows"] == rows_s)
+        r_pef = agg("esvit_patch_embed_fwd", lambda t: t["B"] * (3 * t["H"] * t["W"] * 4 + (t["H"] // 4) * (t["W"] // 4) * t["E"] * 4),
+                    "patch_embed_fwd2_kernel (all launches of a step)")
+        r_peb = agg("esvit_patch_embed_bwd", lambda t: t["B"] * (3 * t["H"] * t["W"] * 4 + (t["H"] // 4) * (t["W"] // 4) * t["E"] * 4),
+                    "patch_embed_bwd2_kernel (all launches of a step)")
+        for r, key in ((g_fwd, "gemm_bf16"), (g_mul, "gemm_mul_colsum"), (g_wgr, "gemm_wgrad"), (r_lnf, "add_ln_fwd"), (r_lnb, "add_ln_bwd")):
+            if r and key in traffic:
+                r["traffic"] = traffic[key]
+        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm, r_gemm2, g_fwd, g_dgr, g_mul, g_wgr, r_lnf, r_lnb, r_cef, r_pef, r_peb) if r]
         if cands:
             cands.sort(key=lambda r: -r["ms_per_step"])
             roofline, roofline_others = cands[0], cands[1:]
+
+    # whole step against the dense bf16 tensor roofline: algorithmic FLOPs per image-step of SURVEY.md 8(a)
+    GFLOP_PER_IMAGE = {("swin_tiny_w7", 8): 154.4, ("swin_small_w14", 10): 429.3, ("swin_base_w14", 10): 715.5}
+    step_roofline = None
+    gf = GFLOP_PER_IMAGE.get((args.arch, n_local)) if args.out_dim == 65536 else None
+    if gf:
+        pk = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = gf * value / 1e3 / world  # TFLOP/s per GPU
+        step_roofline = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+                         "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
+                         "gflop_per_image_step": gf}
 
     if args.profile and rank == 0:
         step.use_cuda_graph = False
@@ -542,7 +595,7 @@ def main():
                           "l2": "per-step working set (>10 GB of activations/logits) >> 126 MB L2; no explicit flush"},
                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_others": roofline_others,
                "cpu_baseline": cpu_baseline, "parity_check": parity_check, "gpu_reference": gpu_reference,
-               "peak_mem_gib": own_mem_gib, "loss": last_loss}
+               "step_roofline": step_roofline, "peak_mem_gib": own_mem_gib, "loss": last_loss}
         try:  # SURVEY.md 8(d) second metric; never allowed to break the contract line
             out["window_attention_core"] = attention_core_tflops(timed, n_eager) if timed else None
         except Exception as ex:  # noqa: BLE001

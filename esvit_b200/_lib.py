@@ -117,9 +117,15 @@ _META = {
     "esvit_gemm_bias_act": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7])},
     "esvit_gemm_mul_colsum": lambda a: {"M": int(a[6]), "N": int(a[7]), "K": int(a[8])},
     "esvit_gemm_bf16": lambda a: {"M": int(a[5]), "N": int(a[6]), "K": int(a[7]), "b_mn": int(a[9]), "act": int(a[10]),
-                                  "pre": a[4] is not None and getattr(a[4], "value", None) is not None},
+                                  "pre": a[4] is not None and a[4].value is not None},
     "esvit_gemm_mul_colsum2": lambda a: {"M": int(a[6]), "N": int(a[7]), "K": int(a[8])},
     "esvit_gemm_wgrad": lambda a: {"T": int(a[4]), "N": int(a[5]), "K": int(a[6])},
+    "esvit_add_ln_fwd": lambda a: {"T": int(a[-3]), "C": int(a[-2]), "has_x": a[0] is not None and a[0].value is not None,
+                                   "has_delta": a[1] is not None and a[1].value is not None},
+    "esvit_add_ln_bwd": lambda a: {"T": int(a[-3]), "C": int(a[-2])},
+    "esvit_dino_ce_fwd": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
+    "esvit_patch_embed_fwd": lambda a: {"B": int(a[-5]), "H": int(a[-4]), "W": int(a[-3]), "E": int(a[-2])},
+    "esvit_patch_embed_bwd": lambda a: {"B": int(a[-5]), "H": int(a[-4]), "W": int(a[-3]), "E": int(a[-2])},
 }
 
 

@@ -66,6 +66,66 @@ def full_metrics():
     print("\n".join(out))
 
 
+def kernel_cases():
+    """gpurun_out/k_<case>.ncu-rep (scripts/ncu_capture_r2.sh) -> profiles/<tag>_ncu_kernels.txt + profiles/ncu_traffic.json
+    (what bench.py's roofline.traffic reads: measured DRAM bytes of the launch next to its algorithmic bytes)."""
+    import json
+    cases = json.load(open(os.path.join(ROOT, "gpurun_out", "ncu_cases.json")))
+    try:
+        commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+    except Exception:
+        commit = "?"
+    out = ["# ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <n> -c 1 python scripts/ncu_kernels.py <case>",
+           "# one launch of each hot kernel at a known shape of the Swin-T B=64 step; algorithmic bytes / flops from scripts/ncu_kernels.py"]
+    traffic = {}
+    for case, meta in cases.items():
+        rep = os.path.join(ROOT, "gpurun_out", f"k_{case}.ncu-rep")
+        if not os.path.isfile(rep):
+            continue
+        r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+        rows = list(csv.reader(io.StringIO(r.stdout)))
+        if len(rows) < 3:
+            continue
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+
+        def num(key):
+            if key not in d:
+                return None
+            v, u = d[key]
+            x = float(v.replace(",", ""))
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3,
+                    "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}.get(u, 1.0)
+            return x * mult
+        dram = (num("dram__bytes_read.sum") or 0.0) + (num("dram__bytes_write.sum") or 0.0)
+        dur = num("gpu__time_duration.sum")
+        out.append(f"== {case}: {meta['note']}")
+        out.append(f"   Kernel Name: {d.get('Kernel Name', ('?',))[0][:160]}")
+        for k in KEYS:
+            if k in d:
+                out.append(f"   {k}: {d[k][0]} {d[k][1]}")
+        out.append(f"   algorithmic bytes {meta['algorithmic_bytes'] / 1e6:.1f} MB, measured DRAM traffic {dram / 1e6:.1f} MB "
+                   f"(x{dram / max(meta['algorithmic_bytes'], 1):.2f}); under ncu: {dur * 1e6:.1f} us = "
+                   f"{meta['algorithmic_bytes'] / dur / 1e9:.0f} GB/s algorithmic"
+                   + (f", {meta['algorithmic_flops'] / dur / 1e12:.0f} TFLOP/s" if meta["algorithmic_flops"] else ""))
+        traffic[case] = {"ncu_launch": f"{d.get('Kernel Name', ('?',))[0][:80]} | {meta['note']}", "dram_bytes": dram,
+                         "algorithmic_bytes": meta["algorithmic_bytes"], "commit": commit}
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_kernels.txt"), "w").write("\n".join(out) + "\n")
+    # keys bench.py looks up
+    alias = {"window_attn_bwd": "attn_bwd7_s0", "window_attn_fwd": "attn_fwd7_s0", "dino_ce_bwd": "dino_ce_bwd",
+             "gemm_bias_act": "gemm_gelu_fc1_0", "gemm_mul_colsum": "gemm_mul_fc2dgrad_0", "gemm_bf16": "gemm_fwd_qkv0",
+             "gemm_wgrad": "gemm_wgrad_qkv0", "add_ln_bwd": "add_ln_bwd_96", "add_ln_fwd": "add_ln_fwd_96"}
+    for k, c in alias.items():
+        if c in traffic:
+            traffic[k] = traffic[c]
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+    print("\n".join(out))
+
+
 if __name__ == "__main__":
-    launch_summary()
-    full_metrics()
+    if os.path.isfile(os.path.join(ROOT, "gpurun_out", "launches.csv")) and "--no-list" not in sys.argv:
+        launch_summary()
+    if "--kernels" in sys.argv:
+        kernel_cases()
+    else:
+        full_metrics()
