@@ -22,6 +22,7 @@
 
 #include "wa_common.cuh"
 #include "window_attn7.cuh"
+#include "window_attn7_tc.cuh"
 #include "window_attn14.cuh"
 
 namespace wa {
@@ -82,6 +83,25 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
   if (ws == 7) {
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
     if (!bias_ready) wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
+    static const int use_tc = [] { const char* e = getenv("ESVIT_ATTN_TC"); return e ? atoi(e) : 0; }();
+    if (use_tc) {
+      // tcgen05 / TMEM forward core: one persistent CTA per SM, head on blockIdx.x, pairs of windows on blockIdx.y
+      const size_t smem_tc = wa::tc::fwd7_tc_smem();
+      cudaError_t e = wa::opt_in_smem(wa::tc::window_attn_fwd7_tc_kernel<true>, smem_tc);
+      if (e == cudaSuccess) e = wa::opt_in_smem(wa::tc::window_attn_fwd7_tc_kernel<false>, smem_tc);
+      if (e != cudaSuccess) return (int)e;
+      const int npairs = (nwin + 1) / 2;
+      int gy = esvit_num_sms() / nH;
+      if (gy < 1) gy = 1;
+      const char* ge = getenv("ESVIT_ATTN_GY");
+      if (ge && atoi(ge) > 0) gy = atoi(ge);
+      if (gy > npairs) gy = npairs;
+      if (shift > 0)
+        wa::tc::window_attn_fwd7_tc_kernel<true><<<dim3(nH, gy), wa::tc::NTHREADS, smem_tc, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
+      else
+        wa::tc::window_attn_fwd7_tc_kernel<false><<<dim3(nH, gy), wa::tc::NTHREADS, smem_tc, st>>>(q, qb, bias_ws, (bf16*)out, lse, g, scale, nwin);
+      ESVIT_LAUNCH_CHECK();
+    }
     const size_t smem = wa::fwd7_smem();
     const int gx = wa::windows_grid(nwin, nH, 16);  // persistent: ~4 waves of 4 resident CTAs per SM
     if (shift > 0)

@@ -11,7 +11,7 @@ from esvit_b200 import ops  # noqa: E402
 d = torch.device("cuda:0")
 shapes = [(128, 56, 96, 3), (512, 24, 96, 3), (128, 28, 192, 6), (512, 12, 192, 6), (128, 14, 384, 12), (512, 6, 384, 12),
           (128, 7, 768, 24), (512, 3, 768, 24)]
-for dbg in ("0", "1", "2"):
+for dbg in (("0",) if os.environ.get("ESVIT_ATTN_TC") or os.environ.get("ESVIT_ATTN_ONLY0") else ("0", "1", "2")):
     os.environ["ESVIT_ATTN_DBG"] = dbg
     tot_f = tot_b = 0.0
     for (B, H, C, nH) in shapes:

@@ -16,3 +16,9 @@ tail -5 gpurun_out/r2c_bench_gemm2.err
 timeout 600 python bench.py --steps 20 --warmup 3 --no-gpu-reference --no-cpu-baseline --profile gpurun_out/r2c_prof_lib.txt > gpurun_out/r2c_bench_lib.json 2> gpurun_out/r2c_bench_lib.err
 echo "bench lib rc=$?"
 tail -c 600 gpurun_out/r2c_bench_lib.json
+# tcgen05 attention forward core (ESVIT_ATTN_TC=1): block-level parity tests + micro-benchmark next to the mma.sync kernel
+ESVIT_ATTN_TC=1 timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_real_shapes_gpu.py -q -m gpu -k "swin_block and not w14" > gpurun_out/r2c_pytest_attn_tc.log 2>&1
+echo "pytest ATTN_TC rc=$?"; tail -12 gpurun_out/r2c_pytest_attn_tc.log
+ESVIT_ATTN_TC=1 timeout 300 python scripts/bench_attn.py > gpurun_out/r2c_attn_tc.txt 2>&1
+ESVIT_ATTN_ONLY0=1 timeout 300 python scripts/bench_attn.py > gpurun_out/r2c_attn_base.txt 2>&1
+tail -3 gpurun_out/r2c_attn_tc.txt; tail -3 gpurun_out/r2c_attn_base.txt
