@@ -663,12 +663,29 @@ static int launch(const Call& c, int epi, int cg, int bn, void* stream, int* gri
   return ESVIT_ERR_BAD_ARG;
 }
 
-// tile shape policy (overridable per call through `tile` = forced_splits * 10000 + cg * 1000 + bn, 0 = automatic)
-static void pick_tile(long long M, int N, int tile, int* cg, int* bn) {
+// Tile shape policy, fitted to scripts/bench_gemm2.py on B200 (profiles/r02_gemm2_microbench.txt); overridable per call
+// through `tile` = forced_splits * 10000 + cg * 1000 + bn (0 = automatic).
+//   memory-bound shapes (small K, M = all tokens: stages 0 / 1) want MANY small tiles in flight: single CTAs, BN = 128;
+//   compute-bound shapes (K >= 512 or enough work per output byte) want CTA pairs with 256 x 256 tiles (B read once per
+//   pair, 64 B/clk/SM of operand traffic instead of 128).  `outs` = [M,N] bf16 streams moved besides the operands.
+static void pick_tile(long long M, int N, int K, int epi, int tile, int* cg, int* bn) {
   tile %= 10000;
   if (tile > 0) { *cg = tile / 1000; *bn = tile % 1000; return; }
-  *bn = N > 128 ? 256 : 128;
-  *cg = M > 128 ? 2 : 1;
+  const int wide = N > 128 ? 256 : 128;
+  if (M <= 128) { *cg = 1; *bn = wide; return; }
+  const double outs = (epi == EPI_GELU || epi == EPI_MUL) ? 2.0 : 1.0;
+  const double inten = (double)N * K / (K + outs * N);          // ~ MACs per byte moved for M >> N, K
+  const double lo = outs > 1.5 ? 80.0 : 100.0, hi = outs > 1.5 ? 150.0 : 260.0;
+  if (K >= 512 || inten >= hi) { *cg = 2; *bn = wide; }
+  else if (inten >= lo) { *cg = 1; *bn = wide; }
+  else { *cg = 1; *bn = 128; }
+}
+// weight gradient (GEMM M = out features, N = in features, contraction over tokens)
+static void pick_tile_wgrad(int Nout, int Kin, int tile, int* cg, int* bn) {
+  tile %= 10000;
+  if (tile > 0) { *cg = tile / 1000; *bn = tile % 1000; return; }
+  *bn = Kin > 128 ? 256 : 128;
+  *cg = Nout > 128 ? 2 : 1;
 }
 
 }  // namespace tg2
@@ -689,7 +706,7 @@ ESVIT_API int esvit_gemm_bf16(const void* a, const void* b, const float* bias, v
   c.p.a_mn = a_mn ? 1 : 0; c.p.b_mn = b_mn ? 1 : 0; c.p.has_pre = (act == 1 && pre) ? 1 : 0; c.p.splits = 1;
   c.p.kb_per_split = (K + tg2::BK - 1) / tg2::BK;
   int cg, bn;
-  tg2::pick_tile(M, N, tile, &cg, &bn);
+  tg2::pick_tile(M, N, K, (act && pre) ? tg2::EPI_GELU : tg2::EPI_BIAS, tile, &cg, &bn);
   return tg2::launch(c, act ? tg2::EPI_GELU : tg2::EPI_BIAS, cg, bn, stream);
 }
 
@@ -705,7 +722,7 @@ ESVIT_API int esvit_gemm_mul_colsum2(const void* a, const void* b, const void* m
   c.p.bias = nullptr; c.p.colsum = ws; c.p.part = nullptr; c.p.M = (int)M; c.p.N = N; c.p.K = K;
   c.p.a_mn = 0; c.p.b_mn = b_mn ? 1 : 0; c.p.has_pre = 0; c.p.splits = 1; c.p.kb_per_split = (K + tg2::BK - 1) / tg2::BK;
   int cg, bn, rows = 0;
-  tg2::pick_tile(M, N, tile, &cg, &bn);
+  tg2::pick_tile(M, N, K, tg2::EPI_MUL, tile, &cg, &bn);
   const int rc = tg2::launch(c, tg2::EPI_MUL, cg, bn, stream, &rows);
   if (rc != 0) return rc;
   tg2::colsum_fold_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, rows, N, colsum);
@@ -713,8 +730,8 @@ ESVIT_API int esvit_gemm_mul_colsum2(const void* a, const void* b, const void* m
 }
 
 // Weight gradient of a Linear: dw[N,K] (fp32) (+)= dy[T,N]^T . x[T,K]   (dy, x bf16 row-major, read as they lie through
-// MN-major TMA boxes).  Split over T across the persistent CTAs; partial tiles go to ws (fp32, esvit_gemm_wgrad_ws_floats
-// elements) and are folded in a fixed order: bit-reproducible, no atomics.  N, K multiples of 8, T multiple of 8.
+// MN-major TMA boxes; any T).  Split over T across the persistent CTAs; partial tiles go to ws (fp32, esvit_gemm_wgrad_ws_floats
+// elements) and are folded in a fixed order: bit-reproducible, no atomics.  N, K multiples of 8.
 static long long wgrad_ws_floats(int N, int K) {
   const int tiles = ((N + 255) / 256) * ((K + 255) / 256);   // the fewest output tiles any tile shape yields
   long long splits = (2LL * 160 + tiles - 1) / tiles;
@@ -729,10 +746,10 @@ ESVIT_API int esvit_gemm_wgrad_ws_floats(int N, int K) {
 }
 ESVIT_API int esvit_gemm_wgrad(const void* dy, const void* x, float* dw, float* ws, long long T, int N, int K,
                                int accumulate, int tile, void* stream) {
-  if (T <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8) || (T % 8) || T > 0x7fffffffLL || !ws) return ESVIT_ERR_BAD_ARG;
+  if (T <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8) || T > 0x7fffffffLL || !ws) return ESVIT_ERR_BAD_ARG;
   // GEMM view: M = N (out features), N = K (in features), contraction = T
   int cg, bn;
-  tg2::pick_tile(N, K, tile, &cg, &bn);
+  tg2::pick_tile_wgrad(N, K, tile, &cg, &bn);
   const int m_tiles = (N + tg2::BM * cg - 1) / (tg2::BM * cg), n_tiles = (K + bn - 1) / bn;
   const int tiles = m_tiles * n_tiles;
   const int k_blocks = (int)((T + tg2::BK - 1) / tg2::BK);
@@ -756,4 +773,16 @@ ESVIT_API int esvit_gemm_wgrad(const void* dy, const void* x, float* dw, float* 
   const long long n4 = (long long)N * K / 4;
   tg2::split_fold_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ws, splits, n4, dw, accumulate);
   ESVIT_LAUNCH_CHECK();
+}
+
+// ---- first-generation entry points (round 1), now served by the same kernel family -------------------------------
+// out[M,N] (bf16) = act(a[M,K] @ w[N,K]^T + bias[N]); act 1 = GELU (pre, if not NULL, receives gelu'(pre-activation)).
+ESVIT_API int esvit_gemm_bias_act(const void* a, const void* w, const float* bias, void* out, void* pre, long long M,
+                                  int N, int K, int act, void* stream) {
+  return esvit_gemm_bf16(a, w, bias, out, pre, M, N, K, 0, 0, act, 0, stream);
+}
+// out[M,N] (bf16) = (a[M,K] @ w[N,K]^T) * mult[M,N];  colsum[N] (fp32) += column sums of out; ws fp32 [160 * N].
+ESVIT_API int esvit_gemm_mul_colsum(const void* a, const void* w, const void* mult, void* out, float* colsum, float* ws,
+                                    long long M, int N, int K, void* stream) {
+  return esvit_gemm_mul_colsum2(a, w, mult, out, colsum, ws, M, N, K, 0, 0, stream);
 }

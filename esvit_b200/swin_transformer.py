@@ -39,7 +39,7 @@ USE_TCGEN05_FC1 = os.environ.get("ESVIT_TCGEN05_FC1", "1") != "0"
 USE_FUSED_GROUPS = os.environ.get("ESVIT_FUSE_GROUPS", "1") != "0"
 # every Linear (forward, input gradient, weight gradient) on the second-generation tcgen05 GEMM family (esvit_b200.linear)
 # instead of library GEMMs; ESVIT_GEMM2=0 restores the library-GEMM path of round 1
-USE_GEMM2 = os.environ.get("ESVIT_GEMM2", "0") != "0"
+USE_GEMM2 = os.environ.get("ESVIT_GEMM2", "1") != "0"
 
 
 def _trunc_normal_(t: Tensor, std: float = .02) -> Tensor:
