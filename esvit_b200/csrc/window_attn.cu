@@ -23,6 +23,7 @@
 #include "wa_common.cuh"
 #include "window_attn7.cuh"
 #include "window_attn7_tc.cuh"
+#include "window_attn7_tc_bwd.cuh"
 #include "window_attn14.cuh"
 
 namespace wa {
@@ -138,6 +139,27 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
   if (ws == 7) {
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
     if (!bias_ready) wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
+    static const int use_tc = [] { const char* ev = getenv("ESVIT_ATTN_TC"); return ev ? atoi(ev) : 0; }();
+    if (use_tc >= 2) {
+      // tcgen05 / TMEM backward core: one persistent CTA per SM, head on blockIdx.x, pairs of windows on blockIdx.y
+      const size_t smem_tc = wa::tcb::bwd7_tc_smem();
+      cudaError_t e2 = wa::opt_in_smem(wa::tcb::window_attn_bwd7_tc_kernel<true>, smem_tc);
+      if (e2 == cudaSuccess) e2 = wa::opt_in_smem(wa::tcb::window_attn_bwd7_tc_kernel<false>, smem_tc);
+      if (e2 != cudaSuccess) return (int)e2;
+      const int npairs = (nwin + 1) / 2;
+      int gy = esvit_num_sms() / nH;
+      if (gy < 1) gy = 1;
+      const char* ge = getenv("ESVIT_ATTN_GY");
+      if (ge && atoi(ge) > 0) gy = atoi(ge);
+      if (gy > npairs) gy = npairs;
+      if (shift > 0)
+        wa::tcb::window_attn_bwd7_tc_kernel<true><<<dim3(nH, gy), wa::tcb::NTHREADS, smem_tc, st>>>(
+            q, qb, bias_ws, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dbias_table, dqkv_bias, g, scale, nwin);
+      else
+        wa::tcb::window_attn_bwd7_tc_kernel<false><<<dim3(nH, gy), wa::tcb::NTHREADS, smem_tc, st>>>(
+            q, qb, bias_ws, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dbias_table, dqkv_bias, g, scale, nwin);
+      ESVIT_LAUNCH_CHECK();
+    }
     const size_t smem = wa::bwd7_smem();
     cudaError_t e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<true>, smem);
     if (e == cudaSuccess) e = wa::opt_in_smem(wa::window_attn_bwd7_kernel<false>, smem);

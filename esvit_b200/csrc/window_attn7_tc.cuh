@@ -4,17 +4,19 @@
 // of one UMMA tile, so every TMEM lane is one query row and the softmax needs no shuffles at all.
 //
 //   gather warps (4)  cp.async the q / k / v rows of the pair's slots (pad / roll / partition folded into the addressing,
-//                     padded slots = the qkv bias, slots >= 49 zero) into 128B-swizzled K-major tiles, 2 stages
+//                     padded slots = the qkv bias, slots >= 49 zero) into 128B-swizzled tiles [Q] and [K | V] (K and V of a
+//                     slot share one 128-byte row), 3 stages, with an L2 prefetch three pairs ahead
 //   MMA warp (1 thr)  S = Q K^T     tcgen05.mma M=128 N=128 K=32  -> TMEM   (both windows at once; only the two 64 x 64
 //                                                                           diagonal blocks are read back)
-//                     O = P V       tcgen05.mma M=128 N=64  K=128 -> TMEM   (P from smem, V read MN-major as it lies)
-//   row warps (4)     tcgen05.ld of the thread's own score row (64 columns of its window) -> + rel-pos bias held in
-//                     REGISTERS for the whole kernel -> + shift mask -> max / ex2 / sum in registers -> normalised P in bf16
-//                     to the swizzled A-operand tile -> later tcgen05.ld of O, bf16, scatter to token order.
-// S and O are double-buffered in TMEM (2 x 128 + 2 x 64 columns) and P in shared memory, so the MMAs of pair i+1 run
-// under the softmax of pair i; the output epilogue of pair i-1 is deferred behind the softmax of pair i, which hides
-// the P V latency.  Same math as window_attn_fwd7_kernel (log2-domain scores, P normalised in fp32 then rounded to
-// bf16, natural-log LSE saved for the backward).
+//                     O = P [K|V]   tcgen05.mma M=128 N=64  K=128 -> TMEM   (P from smem; the [K|V] tile read MN-major as it
+//                                                                           lies: columns 32..63 of the result are P V)
+//   row warps (2 x 4) thread = query row; the two quads take alternate pairs, each with its own S / O accumulators in TMEM
+//                     and its own P tile: tcgen05.ld of the row's 64 scores -> + rel-pos bias -> + shift mask -> max / ex2 /
+//                     sum in registers -> normalised P in bf16 to the swizzled A-operand tile -> tcgen05.ld of O -> bf16 ->
+//                     scatter to token order.
+// The block-diagonal P tile ([128 x 128], zero off the two 64 x 64 diagonal blocks) costs 24 KB instead of 32: its two
+// K blocks overlap in a shared zero region.  Same math as window_attn_fwd7_kernel (log2-domain scores, P normalised in
+// fp32 then rounded to bf16, natural-log LSE saved for the backward).
 #pragma once
 #include "wa_common.cuh"
 
@@ -22,12 +24,14 @@ namespace wa {
 namespace tc {
 
 constexpr int ROWS = 128;                 // 2 windows x 64 slots
-constexpr int TILE_B = ROWS * 128;        // bytes of one operand tile: 128 rows x 128 B (a head's 32 channels use 64 B)
-constexpr int STAGE_B = 3 * TILE_B;       // Q | K | V
-constexpr int P_B = 2 * TILE_B;           // P: two 64-column K blocks of [128 rows x 128 B]
-constexpr int NTHREADS = 32 * 9;          // warps 0-3 rows, 4-7 gather, 8 MMA
+constexpr int TILE_B = ROWS * 128;        // bytes of one operand tile: 128 rows x 128 B
+constexpr int STAGE_B = 2 * TILE_B;       // [Q | -] and [K | V]
+constexpr int NSTAGE = 3;
+constexpr int P_B = 3 * 8192;             // block-diagonal P: [data0 | zero | data1], K block kb starts at kb * 8 KB
+constexpr int BIAS_LD = 68;               // floats per row of the staged rel-pos bias (conflict-free float4 reads)
+constexpr int NTHREADS = 32 * 13;         // warps 0-7 rows (2 quads), 8-11 gather, 12 MMA
 constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0, O_COL = 256;     // S[b] at b*128, O[b] at 256 + b*64
+constexpr int BUF_COLS = 192;             // per quad: S 128 columns + O 64 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -110,10 +114,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 struct Smem {
   // byte offsets from the 1024-aligned base
-  static constexpr int STAGES = 0;                       // [2][Q | K | V]
-  static constexpr int P = 2 * STAGE_B;                  // [2][2 K blocks]
-  static constexpr int META = P + 2 * P_B;               // tok [2][128] int, rid [2][128] int
-  static constexpr int BARS = META + 2 * 2 * ROWS * 4;   // 14 mbarriers + tmem ptr
+  static constexpr int STAGES = 0;                               // [3][Q | KV]
+  static constexpr int P = NSTAGE * STAGE_B;                     // [2 quads][24 KB]
+  static constexpr int BIAS = P + 2 * P_B;                       // [64][68] fp32
+  static constexpr int META = BIAS + 64 * BIAS_LD * 4;           // tok [3][128] int, rid [3][128] int
+  static constexpr int BARS = META + 2 * NSTAGE * ROWS * 4;      // mbarriers + tmem ptr
   static constexpr int TOTAL = BARS + 256;
 };
 static size_t fwd7_tc_smem() { return (size_t)Smem::TOTAL + 1024; }
@@ -127,35 +132,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = base + Smem::STAGES;
   uint8_t* pbuf = base + Smem::P;
-  int* tokb = reinterpret_cast<int*>(base + Smem::META);  // [2][128]
-  int* ridb = tokb + 2 * ROWS;                            // [2][128]
+  float* bias_s = reinterpret_cast<float*>(base + Smem::BIAS);
+  int* tokb = reinterpret_cast<int*>(base + Smem::META);  // [3][128]
+  int* ridb = tokb + NSTAGE * ROWS;                       // [3][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + Smem::BARS);
-  uint64_t* full_qkv = bars;        // [2] count 128 (gather threads)
-  uint64_t* empty_qkv = bars + 2;   // [2] count 1   (MMA commit after P V)
-  uint64_t* s_full = bars + 4;      // [2] count 1   (MMA commit)
-  uint64_t* s_free = bars + 6;      // [2] count 4   (row warps)
-  uint64_t* p_full = bars + 8;      // [2] count 4   (row warps)
-  uint64_t* o_full = bars + 10;     // [2] count 1   (MMA commit)
-  uint64_t* o_free = bars + 12;     // [2] count 4   (row warps)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* full_qkv = bars;        // [3] count 128 (gather threads)
+  uint64_t* empty_qkv = bars + 3;   // [3] count 1   (MMA commit after P V)
+  uint64_t* s_full = bars + 6;      // [2] count 1   (MMA commit)
+  uint64_t* s_free = bars + 8;      // [2] count 4   (row warps of the quad)
+  uint64_t* p_full = bars + 10;     // [2] count 4
+  uint64_t* o_full = bars + 12;     // [2] count 1   (MMA commit)
+  uint64_t* o_free = bars + 14;     // [2] count 4
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int h = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = (nwin_total + 1) >> 1;
-  const int n_items = blockIdx.y < npairs ? (npairs - 1 - (int)blockIdx.y) / (int)gridDim.y + 1 : 0;
+  const int n_items = (int)blockIdx.y < npairs ? (npairs - 1 - (int)blockIdx.y) / (int)gridDim.y + 1 : 0;
 
-  // one-time setup: zero every operand tile (the unused 64 B of each 128 B row feed the N = 64 P V MMA; the off-diagonal
-  // P blocks must be 0 and are never written again), barriers, TMEM
-  for (int i = threadIdx.x; i < (2 * STAGE_B + 2 * P_B) / 16; i += NTHREADS)
+  // one-time setup: zero every operand tile (unused half rows and the shared zero region of P feed the MMAs), stage this
+  // head's rel-pos bias, barriers, TMEM
+  for (int i = threadIdx.x; i < (NSTAGE * STAGE_B + 2 * P_B) / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 64 * 16; i += NTHREADS) {
+    const int row = i >> 4, c4 = (i & 15) * 4;
+    *reinterpret_cast<float4*>(bias_s + row * BIAS_LD + c4) =
+        __ldg(reinterpret_cast<const float4*>(bexp + (long long)h * 4096 + (row < NT ? row : 0) * 64 + c4));
+  }
   if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_qkv[i], 128); mbar_init(&empty_qkv[i], 1); }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&full_qkv[i], 128); mbar_init(&empty_qkv[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
@@ -165,183 +176,198 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 8 && warp < 12) {
     // ===================== gather warps =====================
-    const int t = threadIdx.x - 128;
+    const int t = threadIdx.x - 256;
     const int c16 = t & 3;  // 4 adjacent lanes cover one 64-byte (slot, q|k|v) segment
     uint4 bchunk[3];
 #pragma unroll
     for (int part = 0; part < 3; part++)
       bchunk[part] = __ldg(reinterpret_cast<const uint4*>(qkv_bias + part * g.C + h * HD + c16 * 8));
+    // token row of slot r of window pair `pair` (-1 padded slot, -2 no such slot) and its shift region
+    auto slot = [&](int pair, int r, int& tk, int& rd) {
+      const int w = r >> 6, i = r & 63, win = 2 * pair + w;
+      tk = -2; rd = 0;
+      if (win < nwin_total && i < NT) {
+        const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, bb = win / (g.nWx * g.nWy);
+        slot_info<WS>(g, bb, wy, wx, i, tk, rd);
+      }
+    };
     for (int it = 0; it < n_items; it++) {
-      const int b = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const int st_i = it % NSTAGE;
+      const uint32_t ph = (it / NSTAGE) & 1;
       const int pair = blockIdx.y + it * gridDim.y;
-      mbar_wait(&empty_qkv[b], ph ^ 1);
-      uint8_t* st = stages + b * STAGE_B;
+      if (it + NSTAGE < n_items && c16 < 3) {  // L2 prefetch of the pair three ahead: its gather will hit L2, not DRAM
+        const int pf = pair + NSTAGE * gridDim.y;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          int tk, rd;
+          slot(pf, (t >> 2) + 32 * kk, tk, rd);
+          if (tk >= 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
+        }
+      }
+      mbar_wait(&empty_qkv[st_i], ph ^ 1);
+      uint8_t* stq = stages + st_i * STAGE_B;
+      uint8_t* stkv = stq + TILE_B;
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
         const int r = (t >> 2) + 32 * kk;          // row of the pair tile
-        const int w = r >> 6, i = r & 63;
-        const int win = 2 * pair + w;
-        int tk = -1, rd = 0;
-        const bool wexists = win < nwin_total;
-        if (wexists && i < NT) {
-          const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, bb = win / (g.nWx * g.nWy);
-          slot_info<WS>(g, bb, wy, wx, i, tk, rd);
-        }
-        uint8_t* dst = st + r * 128 + ((c16 ^ (r & 7)) * 16);
-        if (wexists && i < NT && tk < 0) {         // padded slot: the qkv bias (the reference pads norm1's output with zeros)
-#pragma unroll
-          for (int part = 0; part < 3; part++) *reinterpret_cast<uint4*>(dst + part * TILE_B) = bchunk[part];
+        int tk, rd;
+        slot(pair, r, tk, rd);
+        const int sw = r & 7;
+        uint8_t* dq = stq + r * 128 + ((c16 ^ sw) * 16);
+        uint8_t* dk = stkv + r * 128 + ((c16 ^ sw) * 16);
+        uint8_t* dv = stkv + r * 128 + (((4 + c16) ^ sw) * 16);
+        if (tk == -1) {                            // padded slot: the qkv bias (the reference pads norm1's output with zeros)
+          *reinterpret_cast<uint4*>(dq) = bchunk[0];
+          *reinterpret_cast<uint4*>(dk) = bchunk[1];
+          *reinterpret_cast<uint4*>(dv) = bchunk[2];
         } else {
           const bf16* src = qkv + (long long)(tk >= 0 ? tk : 0) * 3 * g.C + h * HD + c16 * 8;
           const int nbytes = tk >= 0 ? 16 : 0;     // slots >= 49 / missing second window: zero fill
-#pragma unroll
-          for (int part = 0; part < 3; part++) cp_async16(dst + part * TILE_B, src + part * g.C, nbytes);
+          cp_async16(dq, src, nbytes);
+          cp_async16(dk, src + g.C, nbytes);
+          cp_async16(dv, src + 2 * g.C, nbytes);
         }
         if (c16 == 0) {
-          tokb[b * ROWS + r] = (wexists && i < NT) ? tk : -2;  // -1: padded slot of a real window, -2: no such slot
-          ridb[b * ROWS + r] = rd;
+          tokb[st_i * ROWS + r] = tk;
+          ridb[st_i * ROWS + r] = rd;
         }
       }
       cp_async_commit();
       cp_async_wait<0>();
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
-      mbar_arrive(&full_qkv[b]);
+      mbar_arrive(&full_qkv[st_i]);
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc(128, 128, false);
       const uint32_t idesc_o = make_idesc(128, 64, true);
       for (int it = 0; it <= n_items; it++) {
         if (it < n_items) {  // S(it) = Q K^T
-          const int b = it & 1;
-          const uint32_t ph = (it >> 1) & 1;
-          mbar_wait(&full_qkv[b], ph);
-          mbar_wait(&s_free[b], ph ^ 1);
+          const int b = it & 1, st_i = it % NSTAGE;
+          mbar_wait(&full_qkv[st_i], (it / NSTAGE) & 1);
+          mbar_wait(&s_free[b], ((it >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t q = smem_u32(stages + b * STAGE_B);
+          const uint32_t q = smem_u32(stages + st_i * STAGE_B);
           const uint64_t adesc = make_desc(q, false), bdesc = make_desc(q + TILE_B, false);
 #pragma unroll
-          for (int k = 0; k < 2; k++) umma(tmem_base + S_COL + b * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k);
+          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, adesc + 2 * k, bdesc + 2 * k, idesc_s, k);
           umma_commit(&s_full[b]);
         }
-        if (it > 0) {        // O(it-1) = P V
-          const int b = (it - 1) & 1;
-          const uint32_t ph = ((it - 1) >> 1) & 1;
+        if (it > 0) {        // O(it-1) = P [K|V]
+          const int j = it - 1, b = j & 1, st_j = j % NSTAGE;
+          const uint32_t ph = (j >> 1) & 1;
           mbar_wait(&p_full[b], ph);
           mbar_wait(&o_free[b], ph ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t pa = smem_u32(pbuf + b * P_B), va = smem_u32(stages + b * STAGE_B + 2 * TILE_B);
+          const uint32_t pa = smem_u32(pbuf + b * P_B), va = smem_u32(stages + st_j * STAGE_B + TILE_B);
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            const uint64_t adesc = make_desc(pa + (k >> 2) * TILE_B, false) + 2 * (k & 3);   // 16 keys = 32 B along K
-            const uint64_t bdesc = make_desc(va, true) + (uint64_t)((2048 >> 4) * k);       // 16 key rows of V
-            umma(tmem_base + O_COL + b * 64, adesc, bdesc, idesc_o, k);
+            const uint64_t adesc = make_desc(pa + (k >> 2) * 8192, false) + 2 * (k & 3);   // 16 keys = 32 B along K
+            const uint64_t bdesc = make_desc(va, true) + (uint64_t)((2048 >> 4) * k);     // 16 key rows of [K|V]
+            umma(tmem_base + b * BUF_COLS + 128, adesc, bdesc, idesc_o, k);
           }
           umma_commit(&o_full[b]);
-          umma_commit(&empty_qkv[b]);  // Q / K / V tiles of this stage are free once these MMAs have read them
+          umma_commit(&empty_qkv[st_j]);  // the stage's tiles are free once these MMAs have read them
         }
       }
     }
   } else {
-    // ===================== row warps: thread = query row =====================
-    const int r = threadIdx.x;                 // 0..127 = TMEM lane
+    // ===================== row warps: two quads, thread = query row =====================
+    const int quad = warp >> 2, qw = warp & 3;
+    const int r = qw * 32 + lane;              // 0..127 = TMEM lane
     const int w = r >> 6, i = r & 63;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + quad * BUF_COLS;
     const float c = scale * LOG2E;
-    // rel-pos bias row of this slot (log2 domain, -inf beyond the 49 real keys): registers for the whole kernel
-    float bias[64];
-    {
-      const float4* bp = reinterpret_cast<const float4*>(bexp + (long long)h * 4096 + (i < NT ? i : 0) * 64);
+    const float* brow = bias_s + i * BIAS_LD;
+    uint8_t* prow = pbuf + quad * P_B + w * 8192 + r * 128;
+    for (int it = quad; it < n_items; it += 2) {
+      const int st_i = it % NSTAGE;
+      const uint32_t ph = (it >> 1) & 1;
+      const int pair = blockIdx.y + it * gridDim.y;
+      mbar_wait(&full_qkv[st_i], (it / NSTAGE) & 1);   // tok / rid of this stage are written
+      const int tok = tokb[st_i * ROWS + r];
+      int rid_r = 0;
+      if (SHIFT) rid_r = ridb[st_i * ROWS + r];
+      mbar_wait(&s_full[quad], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      uint32_t v[64];
+      tmem_ld32(taddr + w * 64, v);
+      tmem_ld32(taddr + w * 64 + 32, v + 32);
+      tmem_ld_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[quad]);
+      float x[64];
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const float4 v4 = __ldg(bp + j);
-        bias[4 * j] = v4.x; bias[4 * j + 1] = v4.y; bias[4 * j + 2] = v4.z; bias[4 * j + 3] = v4.w;
-      }
-    }
-    int tok_prev = -2;
-    for (int it = 0; it <= n_items; it++) {
-      int tok_cur = -2;
-      if (it < n_items) {
-        const int b = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        const int pair = blockIdx.y + it * gridDim.y;
-        mbar_wait(&full_qkv[b], ph);           // tok / rid of this stage are written
-        tok_cur = tokb[b * ROWS + r];
-        int rid_r = 0;
-        if (SHIFT) rid_r = ridb[b * ROWS + r];
-        mbar_wait(&s_full[b], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t v[64];
-        tmem_ld32(lane_addr + S_COL + b * 128 + w * 64, v);
-        tmem_ld32(lane_addr + S_COL + b * 128 + w * 64 + 32, v + 32);
-        tmem_ld_wait();
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[b]);
-        float x[64];
-        float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 64; j++) {
-          x[j] = fmaf(__uint_as_float(v[j]), c, bias[j]);
-          if (SHIFT) {
-            if (j < NT && ridb[b * ROWS + w * 64 + j] != rid_r) x[j] += -100.f * LOG2E;
-          }
-          m = fmaxf(m, x[j]);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; j++) {
-          x[j] = ex2(x[j] - m);
-          s += x[j];
-        }
-        const float inv = __fdividef(1.f, s);
-        // normalised P (fp32 -> bf16, as the reference under autocast) into the diagonal block of the A-operand tile
-        uint8_t* prow = pbuf + b * P_B + w * TILE_B + r * 128;
-#pragma unroll
-        for (int ch = 0; ch < 8; ch++) {
-          float p8[8];
-#pragma unroll
-          for (int e = 0; e < 8; e++) p8[e] = x[ch * 8 + e] * inv;
-          *reinterpret_cast<bf16x8*>(prow + ((ch ^ (r & 7)) * 16)) = pack8(p8);
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[b]);
-        const int win = 2 * pair + w;
-        if (win < nwin_total && i < NT) lse[((long long)win * g.nH + h) * NT + i] = (m + lg2(s)) * LN2;
-      }
-      if (it > 0) {  // deferred epilogue of the previous pair: O -> bf16 -> token order
-        const int b = (it - 1) & 1;
-        const uint32_t ph = ((it - 1) >> 1) & 1;
-        mbar_wait(&o_full[b], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t o[32];
-        tmem_ld32(lane_addr + O_COL + b * 64, o);
-        tmem_ld_wait();
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[b]);
-        if (tok_prev >= 0) {
-          bf16* dst = out + (long long)tok_prev * g.C + h * HD;
-#pragma unroll
-          for (int ch = 0; ch < 4; ch++) {
-            float f8[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) f8[e] = __uint_as_float(o[ch * 8 + e]);
-            *reinterpret_cast<bf16x8*>(dst + ch * 8) = pack8(f8);
+      for (int j4 = 0; j4 < 16; j4++) {
+        const float4 b4 = *reinterpret_cast<const float4*>(brow + j4 * 4);
+        x[4 * j4] = fmaf(__uint_as_float(v[4 * j4]), c, b4.x);
+        x[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), c, b4.y);
+        x[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), c, b4.z);
+        x[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), c, b4.w);
+        if (SHIFT) {
+          if (4 * j4 < NT) {
+            const int4 rc = *reinterpret_cast<const int4*>(ridb + st_i * ROWS + w * 64 + 4 * j4);
+            if (rc.x != rid_r) x[4 * j4] += -100.f * LOG2E;
+            if (rc.y != rid_r) x[4 * j4 + 1] += -100.f * LOG2E;
+            if (rc.z != rid_r) x[4 * j4 + 2] += -100.f * LOG2E;
+            if (rc.w != rid_r) x[4 * j4 + 3] += -100.f * LOG2E;
           }
         }
+        m0 = fmaxf(m0, x[4 * j4]); m1 = fmaxf(m1, x[4 * j4 + 1]); m2 = fmaxf(m2, x[4 * j4 + 2]); m3 = fmaxf(m3, x[4 * j4 + 3]);
       }
-      tok_prev = tok_cur;
+      const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4++) {
+        x[4 * j4] = ex2(x[4 * j4] - m); x[4 * j4 + 1] = ex2(x[4 * j4 + 1] - m);
+        x[4 * j4 + 2] = ex2(x[4 * j4 + 2] - m); x[4 * j4 + 3] = ex2(x[4 * j4 + 3] - m);
+        s0 += x[4 * j4]; s1 += x[4 * j4 + 1]; s2 += x[4 * j4 + 2]; s3 += x[4 * j4 + 3];
+      }
+      const float s = (s0 + s1) + (s2 + s3);
+      const float inv = __fdividef(1.f, s);
+      // normalised P (fp32 -> bf16, as the reference under autocast) into this window's diagonal block of the A-operand tile
+      // (the quad's previous P V has completed: its o_full was awaited in the previous iteration's epilogue)
+#pragma unroll
+      for (int ch = 0; ch < 8; ch++) {
+        float p8[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) p8[e] = x[ch * 8 + e] * inv;
+        *reinterpret_cast<bf16x8*>(prow + ((ch ^ (r & 7)) * 16)) = pack8(p8);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[quad]);
+      const int win = 2 * pair + w;
+      if (win < nwin_total && i < NT) lse[((long long)win * g.nH + h) * NT + i] = (m + lg2(s)) * LN2;
+      // epilogue: O -> bf16 -> token order (the other quad's softmax runs meanwhile)
+      mbar_wait(&o_full[quad], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      uint32_t o[32];
+      tmem_ld32(taddr + 128 + 32, o);            // columns 32..63 of P [K|V] = P V
+      tmem_ld_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[quad]);
+      if (tok >= 0) {
+        bf16* dst = out + (long long)tok * g.C + h * HD;
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+          float f8[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) f8[e] = __uint_as_float(o[ch * 8 + e]);
+          *reinterpret_cast<bf16x8*>(dst + ch * 8) = pack8(f8);
+        }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
 }  // namespace tc

@@ -8,5 +8,8 @@ for c in $CASES; do
   k=$(python -c "import json;print(json.load(open('gpurun_out/ncu_cases.json'))['$c']['kernel'])")
   s=2; case $c in dino_ce_*) s=5;; esac
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -f -o gpurun_out/k_$c python scripts/ncu_kernels.py $c > gpurun_out/k_$c.log 2>&1
-  echo "== $c ($k): $(ls -la gpurun_out/k_$c.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
+  # gpurun brings back at most 64 MiB: keep the raw-metric CSV of every capture, the .ncu-rep only for KEEP_REPS
+  ncu -i gpurun_out/k_$c.ncu-rep --page raw --csv > gpurun_out/k_$c.csv 2>/dev/null
+  echo "== $c ($k): $(ls -la gpurun_out/k_$c.ncu-rep 2>/dev/null | awk '{print $5}') bytes, csv $(wc -c < gpurun_out/k_$c.csv)"
+  case " ${KEEP_REPS:-attn_bwd7_s0 gemm_gelu_fc1_0} " in *" $c "*) ;; *) rm -f gpurun_out/k_$c.ncu-rep;; esac
 done
