@@ -5,7 +5,8 @@
 //
 //   gather warps (4)  cp.async the q / k / v rows of the pair's slots (pad / roll / partition folded into the addressing,
 //                     padded slots = the qkv bias, slots >= 49 zero) into 128B-swizzled tiles [Q] and [K | V] (K and V of a
-//                     slot share one 128-byte row), 3 stages, with an L2 prefetch three pairs ahead
+//                     slot share one 128-byte row), 4 stages with 3 pairs of copies in flight per thread, and an L2 prefetch
+//                     four pairs ahead
 //   MMA warp (1 thr)  S = Q K^T     tcgen05.mma M=128 N=128 K=32  -> TMEM   (both windows at once; only the two 64 x 64
 //                                                                           diagonal blocks are read back)
 //                     O = P [K|V]   tcgen05.mma M=128 N=64  K=128 -> TMEM   (P from smem; the [K|V] tile read MN-major as it
@@ -26,7 +27,8 @@ namespace tc {
 constexpr int ROWS = 128;                 // 2 windows x 64 slots
 constexpr int TILE_B = ROWS * 128;        // bytes of one operand tile: 128 rows x 128 B
 constexpr int STAGE_B = 2 * TILE_B;       // [Q | -] and [K | V]
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
+constexpr int GDEPTH = 3;               // cp.async groups (pairs) a gather thread keeps in flight
 constexpr int P_B = 3 * 8192;             // block-diagonal P: [data0 | zero | data1], K block kb starts at kb * 8 KB
 constexpr int BIAS_LD = 68;               // floats per row of the staged rel-pos bias (conflict-free float4 reads)
 constexpr int NTHREADS = 32 * 13;         // warps 0-7 rows (2 quads), 8-11 gather, 12 MMA
@@ -114,10 +116,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 struct Smem {
   // byte offsets from the 1024-aligned base
-  static constexpr int STAGES = 0;                               // [3][Q | KV]
+  static constexpr int STAGES = 0;                               // [NSTAGE][Q | KV]
   static constexpr int P = NSTAGE * STAGE_B;                     // [2 quads][24 KB]
   static constexpr int BIAS = P + 2 * P_B;                       // [64][68] fp32
-  static constexpr int META = BIAS + 64 * BIAS_LD * 4;           // tok [3][128] int, rid [3][128] int
+  static constexpr int META = BIAS + 64 * BIAS_LD * 4;           // tok [NSTAGE][128] int, rid [NSTAGE][128] int
   static constexpr int BARS = META + 2 * NSTAGE * ROWS * 4;      // mbarriers + tmem ptr
   static constexpr int TOTAL = BARS + 256;
 };
@@ -136,14 +138,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
   int* tokb = reinterpret_cast<int*>(base + Smem::META);  // [3][128]
   int* ridb = tokb + NSTAGE * ROWS;                       // [3][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + Smem::BARS);
-  uint64_t* full_qkv = bars;        // [3] count 128 (gather threads)
-  uint64_t* empty_qkv = bars + 3;   // [3] count 1   (MMA commit after P V)
-  uint64_t* s_full = bars + 6;      // [2] count 1   (MMA commit)
-  uint64_t* s_free = bars + 8;      // [2] count 4   (row warps of the quad)
-  uint64_t* p_full = bars + 10;     // [2] count 4
-  uint64_t* o_full = bars + 12;     // [2] count 1   (MMA commit)
-  uint64_t* o_free = bars + 14;     // [2] count 4
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* full_qkv = bars;                 // [NSTAGE] count 128 (gather threads)
+  uint64_t* empty_qkv = bars + NSTAGE;       // [NSTAGE] count 1   (MMA commit after P V)
+  uint64_t* s_full = bars + 2 * NSTAGE;      // [2] count 1   (MMA commit)
+  uint64_t* s_free = s_full + 2;             // [2] count 4   (row warps of the quad)
+  uint64_t* p_full = s_full + 4;             // [2] count 4
+  uint64_t* o_full = s_full + 6;             // [2] count 1   (MMA commit)
+  uint64_t* o_free = s_full + 8;             // [2] count 4
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_full + 10);
 
   const int h = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,60 +186,97 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
 #pragma unroll
     for (int part = 0; part < 3; part++)
       bchunk[part] = __ldg(reinterpret_cast<const uint4*>(qkv_bias + part * g.C + h * HD + c16 * 8));
-    // token row of slot r of window pair `pair` (-1 padded slot, -2 no such slot) and its shift region
-    auto slot = [&](int pair, int r, int& tk, int& rd) {
-      const int w = r >> 6, i = r & 63, win = 2 * pair + w;
+    // per-thread constants: the 4 rows this thread serves (same slot geometry for every pair)
+    int rr[4], iy[4], ix[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      rr[kk] = (t >> 2) + 32 * kk;
+      const int i = rr[kk] & 63;
+      iy[kk] = i / WS;
+      ix[kk] = i - iy[kk] * WS;
+    }
+    // token row of row kk of window pair `pair` (-1 padded slot, -2 no such slot) and its shift region; (bb, wy, wx) of the
+    // pair's two windows are computed once per pair, not per row
+    struct PairGeo { int bb[2], wy[2], wx[2]; bool ok[2]; };
+    auto pair_geo = [&](int pair) {
+      PairGeo pg;
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        const int win = 2 * pair + w;
+        pg.ok[w] = win < nwin_total;
+        pg.wx[w] = win % g.nWx;
+        const int t2 = win / g.nWx;
+        pg.wy[w] = t2 % g.nWy;
+        pg.bb[w] = t2 / g.nWy;
+      }
+      return pg;
+    };
+    auto slot = [&](const PairGeo& pg, int kk, int& tk, int& rd) {
+      const int w = rr[kk] >> 6;
       tk = -2; rd = 0;
-      if (win < nwin_total && i < NT) {
-        const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, bb = win / (g.nWx * g.nWy);
-        slot_info<WS>(g, bb, wy, wx, i, tk, rd);
+      if (pg.ok[w] && iy[kk] < WS) {
+        const int ry = pg.wy[w] * WS + iy[kk], rx = pg.wx[w] * WS + ix[kk];
+        int py = ry + g.shift, px = rx + g.shift;
+        if (py >= g.Hp) py -= g.Hp;
+        if (px >= g.Wp) px -= g.Wp;
+        tk = (py < g.H && px < g.W) ? (pg.bb[w] * g.H + py) * g.W + px : -1;
+        if (g.shift > 0) {
+          const int ay = (ry >= g.Hp - WS) + (ry >= g.Hp - g.shift);
+          const int ax = (rx >= g.Wp - WS) + (rx >= g.Wp - g.shift);
+          rd = ay * 3 + ax;
+        }
       }
     };
-    for (int it = 0; it < n_items; it++) {
-      const int st_i = it % NSTAGE;
-      const uint32_t ph = (it / NSTAGE) & 1;
-      const int pair = blockIdx.y + it * gridDim.y;
-      if (it + NSTAGE < n_items && c16 < 3) {  // L2 prefetch of the pair three ahead: its gather will hit L2, not DRAM
-        const int pf = pair + NSTAGE * gridDim.y;
+    for (int it = 0; it < n_items + GDEPTH; it++) {
+      if (it < n_items) {
+        const int st_i = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        const int pair = blockIdx.y + it * gridDim.y;
+        if (it + NSTAGE < n_items && c16 < 3) {  // L2 prefetch of the pair NSTAGE ahead: its gather will hit L2, not DRAM
+          const PairGeo pf = pair_geo(pair + NSTAGE * gridDim.y);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            int tk, rd;
+            slot(pf, kk, tk, rd);
+            if (tk >= 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
+          }
+        }
+        const PairGeo pg = pair_geo(pair);
+        mbar_wait(&empty_qkv[st_i], ph ^ 1);
+        uint8_t* stq = stages + st_i * STAGE_B;
+        uint8_t* stkv = stq + TILE_B;
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
+          const int r = rr[kk];
           int tk, rd;
-          slot(pf, (t >> 2) + 32 * kk, tk, rd);
-          if (tk >= 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
+          slot(pg, kk, tk, rd);
+          const int sw = r & 7;
+          uint8_t* dq = stq + r * 128 + ((c16 ^ sw) * 16);
+          uint8_t* dk = stkv + r * 128 + ((c16 ^ sw) * 16);
+          uint8_t* dv = stkv + r * 128 + (((4 + c16) ^ sw) * 16);
+          if (tk == -1) {                            // padded slot: the qkv bias (the reference pads norm1's output with zeros)
+            *reinterpret_cast<uint4*>(dq) = bchunk[0];
+            *reinterpret_cast<uint4*>(dk) = bchunk[1];
+            *reinterpret_cast<uint4*>(dv) = bchunk[2];
+          } else {
+            const bf16* src = qkv + (long long)(tk >= 0 ? tk : 0) * 3 * g.C + h * HD + c16 * 8;
+            const int nbytes = tk >= 0 ? 16 : 0;     // slots >= 49 / missing second window: zero fill
+            cp_async16(dq, src, nbytes);
+            cp_async16(dk, src + g.C, nbytes);
+            cp_async16(dv, src + 2 * g.C, nbytes);
+          }
+          if (c16 == 0) {
+            tokb[st_i * ROWS + r] = tk;
+            ridb[st_i * ROWS + r] = rd;
+          }
         }
       }
-      mbar_wait(&empty_qkv[st_i], ph ^ 1);
-      uint8_t* stq = stages + st_i * STAGE_B;
-      uint8_t* stkv = stq + TILE_B;
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        const int r = (t >> 2) + 32 * kk;          // row of the pair tile
-        int tk, rd;
-        slot(pair, r, tk, rd);
-        const int sw = r & 7;
-        uint8_t* dq = stq + r * 128 + ((c16 ^ sw) * 16);
-        uint8_t* dk = stkv + r * 128 + ((c16 ^ sw) * 16);
-        uint8_t* dv = stkv + r * 128 + (((4 + c16) ^ sw) * 16);
-        if (tk == -1) {                            // padded slot: the qkv bias (the reference pads norm1's output with zeros)
-          *reinterpret_cast<uint4*>(dq) = bchunk[0];
-          *reinterpret_cast<uint4*>(dk) = bchunk[1];
-          *reinterpret_cast<uint4*>(dv) = bchunk[2];
-        } else {
-          const bf16* src = qkv + (long long)(tk >= 0 ? tk : 0) * 3 * g.C + h * HD + c16 * 8;
-          const int nbytes = tk >= 0 ? 16 : 0;     // slots >= 49 / missing second window: zero fill
-          cp_async16(dq, src, nbytes);
-          cp_async16(dk, src + g.C, nbytes);
-          cp_async16(dv, src + 2 * g.C, nbytes);
-        }
-        if (c16 == 0) {
-          tokb[st_i * ROWS + r] = tk;
-          ridb[st_i * ROWS + r] = rd;
-        }
+      cp_async_commit();   // (an empty group past the last pair keeps the group arithmetic uniform)
+      if (it >= GDEPTH) {  // the copies of pair it - GDEPTH have landed
+        cp_async_wait<GDEPTH>();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&full_qkv[(it - GDEPTH) % NSTAGE]);
       }
-      cp_async_commit();
-      cp_async_wait<0>();
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
-      mbar_arrive(&full_qkv[st_i]);
     }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================

@@ -39,6 +39,7 @@ constexpr int ROWS = 128;
 constexpr int TILE_B = ROWS * 128;        // 16 KB
 constexpr int STAGE_B = 2 * TILE_B;       // [Q | dO] and [K | V]
 constexpr int NSTAGE = 3;
+constexpr int GDEPTH = 2;               // cp.async groups (pairs) a gather thread keeps in flight
 constexpr int PD_B = 3 * 8192;            // block-diagonal P or dS: [data0 | zero | data1]
 constexpr int BIAS_LD = 68;
 constexpr int NTHREADS = 32 * 11;         // warps 0-7 rows (2 quads), 8-9 gather, 10 MMA
@@ -136,15 +137,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
-  auto slot = [&](int pair, int r, int& tk, int& rd) {  // -1 padded slot, -2 no such slot
-    const int w = r >> 6, i = r & 63, win = 2 * pair + w;
-    tk = -2; rd = 0;
-    if (win < nwin_total && i < NT) {
-      const int wx = win % g.nWx, wy = (win / g.nWx) % g.nWy, bb = win / (g.nWx * g.nWy);
-      slot_info<WS>(g, bb, wy, wx, i, tk, rd);
-    }
-  };
-
   if (warp == 8 || warp == 9) {
     // ===================== gather warps: 64 threads, 4 lanes per 64-byte segment, 8 rows per thread =====================
     const int t = threadIdx.x - 256;
@@ -153,61 +145,103 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
 #pragma unroll
     for (int part = 0; part < 3; part++)
       bchunk[part] = __ldg(reinterpret_cast<const uint4*>(qkv_bias + part * g.C + h * HD + c16 * 8));
-    for (int it = 0; it < n_items; it++) {
-      const int st_i = it % NSTAGE;
-      const uint32_t ph = (it / NSTAGE) & 1;
-      const int pair = blockIdx.y + it * gridDim.y;
-      if (it + NSTAGE < n_items) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
-        const int pf = pair + NSTAGE * gridDim.y;
+    int iy[8], ix[8];   // slot geometry of this thread's 8 rows r = (t >> 2) + 16 kk (the same for every pair)
 #pragma unroll
-        for (int kk = 0; kk < 8; kk++) {
-          int tk, rd;
-          slot(pf, (t >> 2) + 16 * kk, tk, rd);
-          if (tk >= 0) {
-            if (c16 < 3) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
-            else {
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dout + (long long)tk * g.C + h * HD));
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(out + (long long)tk * g.C + h * HD));
+    for (int kk = 0; kk < 8; kk++) {
+      const int i = ((t >> 2) + 16 * kk) & 63;
+      iy[kk] = i / WS;
+      ix[kk] = i - iy[kk] * WS;
+    }
+    struct PairGeo { int bb[2], wy[2], wx[2]; bool ok[2]; };
+    auto pair_geo = [&](int pair) {
+      PairGeo pg;
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        const int win = 2 * pair + w;
+        pg.ok[w] = win < nwin_total;
+        pg.wx[w] = win % g.nWx;
+        const int t2 = win / g.nWx;
+        pg.wy[w] = t2 % g.nWy;
+        pg.bb[w] = t2 / g.nWy;
+      }
+      return pg;
+    };
+    auto slot = [&](const PairGeo& pg, int kk, int& tk, int& rd) {  // -1 padded slot, -2 no such slot
+      const int w = kk >> 2;  // rows 16 kk + (t >> 2): kk < 4 -> window 0, else window 1
+      tk = -2; rd = 0;
+      if (pg.ok[w] && iy[kk] < WS) {
+        const int ry = pg.wy[w] * WS + iy[kk], rx = pg.wx[w] * WS + ix[kk];
+        int py = ry + g.shift, px = rx + g.shift;
+        if (py >= g.Hp) py -= g.Hp;
+        if (px >= g.Wp) px -= g.Wp;
+        tk = (py < g.H && px < g.W) ? (pg.bb[w] * g.H + py) * g.W + px : -1;
+        if (g.shift > 0) {
+          const int ay = (ry >= g.Hp - WS) + (ry >= g.Hp - g.shift);
+          const int ax = (rx >= g.Wp - WS) + (rx >= g.Wp - g.shift);
+          rd = ay * 3 + ax;
+        }
+      }
+    };
+    for (int it = 0; it < n_items + GDEPTH; it++) {
+      if (it < n_items) {
+        const int st_i = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        const int pair = blockIdx.y + it * gridDim.y;
+        if (it + NSTAGE < n_items) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
+          const PairGeo pf = pair_geo(pair + NSTAGE * gridDim.y);
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) {
+            int tk, rd;
+            slot(pf, kk, tk, rd);
+            if (tk >= 0) {
+              if (c16 < 3) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
+              else {
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dout + (long long)tk * g.C + h * HD));
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(out + (long long)tk * g.C + h * HD));
+              }
             }
           }
         }
-      }
-      mbar_wait(&empty_in[st_i], ph ^ 1);
-      uint8_t* t1 = stages + st_i * STAGE_B;   // [Q | dO]
-      uint8_t* t2 = t1 + TILE_B;               // [K | V]
+        const PairGeo pg = pair_geo(pair);
+        mbar_wait(&empty_in[st_i], ph ^ 1);
+        uint8_t* t1 = stages + st_i * STAGE_B;   // [Q | dO]
+        uint8_t* t2 = t1 + TILE_B;               // [K | V]
 #pragma unroll
-      for (int kk = 0; kk < 8; kk++) {
-        const int r = (t >> 2) + 16 * kk;
-        int tk, rd;
-        slot(pair, r, tk, rd);
-        const int sw = r & 7;
-        uint8_t* dq = t1 + r * 128 + ((c16 ^ sw) * 16);
-        uint8_t* dd = t1 + r * 128 + (((4 + c16) ^ sw) * 16);
-        uint8_t* dk = t2 + r * 128 + ((c16 ^ sw) * 16);
-        uint8_t* dv = t2 + r * 128 + (((4 + c16) ^ sw) * 16);
-        if (tk == -1) {          // padded slot: q / k / v = the qkv bias, its output row is cropped away: dO = 0
-          *reinterpret_cast<uint4*>(dq) = bchunk[0];
-          *reinterpret_cast<uint4*>(dk) = bchunk[1];
-          *reinterpret_cast<uint4*>(dv) = bchunk[2];
-          *reinterpret_cast<uint4*>(dd) = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          const long long trow = tk >= 0 ? tk : 0;
-          const bf16* src = qkv + trow * 3 * g.C + h * HD + c16 * 8;
-          const int nbytes = tk >= 0 ? 16 : 0;
-          cp_async16(dq, src, nbytes);
-          cp_async16(dk, src + g.C, nbytes);
-          cp_async16(dv, src + 2 * g.C, nbytes);
-          cp_async16(dd, dout + trow * g.C + h * HD + c16 * 8, nbytes);
-        }
-        if (c16 == 0) {
-          tokb[st_i * ROWS + r] = tk;
-          ridb[st_i * ROWS + r] = rd;
+        for (int kk = 0; kk < 8; kk++) {
+          const int r = (t >> 2) + 16 * kk;
+          int tk, rd;
+          slot(pg, kk, tk, rd);
+          const int sw = r & 7;
+          uint8_t* dq = t1 + r * 128 + ((c16 ^ sw) * 16);
+          uint8_t* dd = t1 + r * 128 + (((4 + c16) ^ sw) * 16);
+          uint8_t* dk = t2 + r * 128 + ((c16 ^ sw) * 16);
+          uint8_t* dv = t2 + r * 128 + (((4 + c16) ^ sw) * 16);
+          if (tk == -1) {          // padded slot: q / k / v = the qkv bias, its output row is cropped away: dO = 0
+            *reinterpret_cast<uint4*>(dq) = bchunk[0];
+            *reinterpret_cast<uint4*>(dk) = bchunk[1];
+            *reinterpret_cast<uint4*>(dv) = bchunk[2];
+            *reinterpret_cast<uint4*>(dd) = make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            const long long trow = tk >= 0 ? tk : 0;
+            const bf16* src = qkv + trow * 3 * g.C + h * HD + c16 * 8;
+            const int nbytes = tk >= 0 ? 16 : 0;
+            cp_async16(dq, src, nbytes);
+            cp_async16(dk, src + g.C, nbytes);
+            cp_async16(dv, src + 2 * g.C, nbytes);
+            cp_async16(dd, dout + trow * g.C + h * HD + c16 * 8, nbytes);
+          }
+          if (c16 == 0) {
+            tokb[st_i * ROWS + r] = tk;
+            ridb[st_i * ROWS + r] = rd;
+          }
         }
       }
       cp_async_commit();
-      cp_async_wait<0>();
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      mbar_arrive(&full_in[st_i]);
+      if (it >= GDEPTH) {
+        cp_async_wait<GDEPTH>();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_arrive(&full_in[(it - GDEPTH) % NSTAGE]);
+      }
     }
   } else if (warp == 10) {
     // ===================== MMA issuer =====================
@@ -288,7 +322,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
           for (int e = 0; e < 8; e++) Dr = fmaf(fo[e], fd[e], Dr);
         }
       }
-      if (tok >= -1) l2 = __ldg(lse + ((long long)(2 * pair + w) * g.nH + h) * NT + i) * LOG2E;
+      // padded query rows (tok == -1) have dO = 0, hence dS = 0 and no dV contribution: P = 0 serves them too (and keeps
+      // an undefined saved LSE of a skipped all-padding tile out of the arithmetic)
+      if (tok >= 0) l2 = __ldg(lse + ((long long)(2 * pair + w) * g.nH + h) * NT + i) * LOG2E;
       mbar_wait(&s_full[quad], ph);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       // the quad's previous dQ / dK / dV GEMMs have completed (g_full awaited below in the previous iteration), so the
