@@ -28,7 +28,7 @@ constexpr int ROWS = 128;                 // 2 windows x 64 slots
 constexpr int TILE_B = ROWS * 128;        // bytes of one operand tile: 128 rows x 128 B
 constexpr int STAGE_B = 2 * TILE_B;       // [Q | -] and [K | V]
 constexpr int NSTAGE = 4;
-constexpr int GDEPTH = 3;               // cp.async groups (pairs) a gather thread keeps in flight
+constexpr int GDEPTH = 2;               // a pair's copies are awaited GDEPTH pairs after they were issued
 constexpr int P_B = 3 * 8192;             // block-diagonal P: [data0 | zero | data1], K block kb starts at kb * 8 KB
 constexpr int BIAS_LD = 68;               // floats per row of the staged rel-pos bias (conflict-free float4 reads)
 constexpr int NTHREADS = 32 * 13;         // warps 0-7 rows (2 quads), 8-11 gather, 12 MMA
@@ -228,6 +228,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
       }
     };
     for (int it = 0; it < n_items + GDEPTH; it++) {
+      // FIRST publish the pair issued GDEPTH iterations ago (its copies have landed), THEN wait for a free stage: the stage
+      // this iteration needs is released by MMAs that themselves wait for that publication (circular otherwise)
+      if (it >= GDEPTH) {
+        cp_async_wait<GDEPTH - 1>();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&full_qkv[(it - GDEPTH) % NSTAGE]);
+      }
       if (it < n_items) {
         const int st_i = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -272,11 +279,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
         }
       }
       cp_async_commit();   // (an empty group past the last pair keeps the group arithmetic uniform)
-      if (it >= GDEPTH) {  // the copies of pair it - GDEPTH have landed
-        cp_async_wait<GDEPTH>();
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
-        mbar_arrive(&full_qkv[(it - GDEPTH) % NSTAGE]);
-      }
     }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================

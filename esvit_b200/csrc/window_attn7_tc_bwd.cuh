@@ -39,7 +39,7 @@ constexpr int ROWS = 128;
 constexpr int TILE_B = ROWS * 128;        // 16 KB
 constexpr int STAGE_B = 2 * TILE_B;       // [Q | dO] and [K | V]
 constexpr int NSTAGE = 3;
-constexpr int GDEPTH = 2;               // cp.async groups (pairs) a gather thread keeps in flight
+constexpr int GDEPTH = 2;               // a pair's copies are awaited GDEPTH pairs after they were issued
 constexpr int PD_B = 3 * 8192;            // block-diagonal P or dS: [data0 | zero | data1]
 constexpr int BIAS_LD = 68;
 constexpr int NTHREADS = 32 * 11;         // warps 0-7 rows (2 quads), 8-9 gather, 10 MMA
@@ -183,6 +183,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       }
     };
     for (int it = 0; it < n_items + GDEPTH; it++) {
+      // FIRST publish the pair issued GDEPTH iterations ago (its copies have landed), THEN wait for a free stage: the stage
+      // this iteration needs is released by GEMMs that themselves wait for that publication (circular otherwise)
+      if (it >= GDEPTH) {
+        cp_async_wait<GDEPTH - 1>();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_arrive(&full_in[(it - GDEPTH) % NSTAGE]);
+      }
       if (it < n_items) {
         const int st_i = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -237,11 +244,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
         }
       }
       cp_async_commit();
-      if (it >= GDEPTH) {
-        cp_async_wait<GDEPTH>();
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_arrive(&full_in[(it - GDEPTH) % NSTAGE]);
-      }
     }
   } else if (warp == 10) {
     // ===================== MMA issuer =====================
