@@ -285,16 +285,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc(128, 128, false);
       const uint32_t idesc_o = make_idesc(128, 64, true);
+      // descriptors of stage 0 / quad 0; other stages and quads differ only in the 14-bit address field (units of 16 B)
+      const uint64_t dq0 = make_desc(smem_u32(stages), false), dk0 = make_desc(smem_u32(stages) + TILE_B, false);
+      const uint64_t dv0 = make_desc(smem_u32(stages) + TILE_B, true), dp0 = make_desc(smem_u32(pbuf), false);
       for (int it = 0; it <= n_items; it++) {
         if (it < n_items) {  // S(it) = Q K^T
           const int b = it & 1, st_i = it % NSTAGE;
           mbar_wait(&full_qkv[st_i], (it / NSTAGE) & 1);
           mbar_wait(&s_free[b], ((it >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t q = smem_u32(stages + st_i * STAGE_B);
-          const uint64_t adesc = make_desc(q, false), bdesc = make_desc(q + TILE_B, false);
+          const uint64_t so = (uint64_t)(st_i * (STAGE_B >> 4));
 #pragma unroll
-          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, adesc + 2 * k, bdesc + 2 * k, idesc_s, k);
+          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, dq0 + so + 2 * k, dk0 + so + 2 * k, idesc_s, k);
           umma_commit(&s_full[b]);
         }
         if (it > 0) {        // O(it-1) = P [K|V]
@@ -303,13 +305,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
           mbar_wait(&p_full[b], ph);
           mbar_wait(&o_free[b], ph ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t pa = smem_u32(pbuf + b * P_B), va = smem_u32(stages + st_j * STAGE_B + TILE_B);
+          const uint64_t pa = dp0 + (uint64_t)(b * (P_B >> 4)), va = dv0 + (uint64_t)(st_j * (STAGE_B >> 4));
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const uint64_t adesc = make_desc(pa + (k >> 2) * 8192, false) + 2 * (k & 3);   // 16 keys = 32 B along K
-            const uint64_t bdesc = make_desc(va, true) + (uint64_t)((2048 >> 4) * k);     // 16 key rows of [K|V]
-            umma(tmem_base + b * BUF_COLS + 128, adesc, bdesc, idesc_o, k);
-          }
+          for (int k = 0; k < 8; k++)   // A: K block k>>2 at +8 KB, 16 keys = 32 B along K; B: 16 key rows of [K|V] = 2 KB
+            umma(tmem_base + b * BUF_COLS + 128, pa + (uint64_t)((k >> 2) * (8192 >> 4) + 2 * (k & 3)), va + (uint64_t)(128 * k), idesc_o, k);
           umma_commit(&o_full[b]);
           umma_commit(&empty_qkv[st_j]);  // the stage's tiles are free once these MMAs have read them
         }

@@ -252,18 +252,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       const uint32_t id_dq = make_idesc2(128, 32, false, true);
       const uint32_t id_dk = make_idesc2(128, 32, true, true);
       const uint32_t id_dv = make_idesc2(128, 64, true, true);
+      // descriptors of stage 0 / quad 0; other stages and quads differ only in the 14-bit address field (units of 16 B)
+      const uint32_t s0 = smem_u32(stages), p0 = smem_u32(pdbuf);
+      const uint64_t t1k = make_desc(s0, false), t2k = make_desc(s0 + TILE_B, false);      // [Q|dO], [K|V] K-major
+      const uint64_t t1m = make_desc(s0, true), t2m = make_desc(s0 + TILE_B, true);        // ... MN-major
+      const uint64_t pm = make_desc(p0, true), dsk = make_desc(p0 + PD_B, false), dsm = make_desc(p0 + PD_B, true);
       for (int it = 0; it <= n_items; it++) {
         if (it < n_items) {  // S(it), dP(it)
           const int b = it & 1, st_i = it % NSTAGE;
           mbar_wait(&full_in[st_i], (it / NSTAGE) & 1);
           mbar_wait(&g_free[b], ((it >> 1) & 1) ^ 1);   // the quad has drained dQ / dK / dV of its previous pair
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t t1 = smem_u32(stages + st_i * STAGE_B), t2 = t1 + TILE_B;
-          const uint64_t a1 = make_desc(t1, false), b2 = make_desc(t2, false);
+          const uint64_t so = (uint64_t)(st_i * (STAGE_B >> 4));
 #pragma unroll
-          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, a1 + 2 * k, b2 + 2 * k, id_s, k);                 // Q K^T
+          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, t1k + so + 2 * k, t2k + so + 2 * k, id_s, k);                 // Q K^T
 #pragma unroll
-          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS + 128, a1 + 4 + 2 * k, b2 + 4 + 2 * k, id_s, k);   // dO V^T
+          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS + 128, t1k + so + 4 + 2 * k, t2k + so + 4 + 2 * k, id_s, k);   // dO V^T
           umma_commit(&s_full[b]);
         }
         if (it > 0) {        // dQ, dK, dV of pair it-1
@@ -271,18 +275,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
           const uint32_t ph = (j >> 1) & 1;
           mbar_wait(&pd_full[b], ph);                   // implies the quad has loaded S / dP: their columns are free
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t t1 = smem_u32(stages + st_j * STAGE_B), t2 = t1 + TILE_B;
-          const uint32_t pa = smem_u32(pdbuf + b * 2 * PD_B), da = pa + PD_B;
+          const uint64_t so = (uint64_t)(st_j * (STAGE_B >> 4)), po = (uint64_t)(b * ((2 * PD_B) >> 4));
           const uint32_t col = tmem_base + b * BUF_COLS;
 #pragma unroll
           for (int k = 0; k < 8; k++)   // dQ = dS K : A K-major (K block k>>2 at +8 KB), B = [K|V] MN-major rows 16k..
-            umma(col, make_desc(da + (k >> 2) * 8192, false) + 2 * (k & 3), make_desc(t2, true) + (uint64_t)(128 * k), id_dq, k);
+            umma(col, dsk + po + (uint64_t)((k >> 2) * (8192 >> 4) + 2 * (k & 3)), t2m + so + (uint64_t)(128 * k), id_dq, k);
 #pragma unroll
           for (int k = 0; k < 8; k++)   // dK = dS^T Q : A = dS MN-major (query rows 16k..), B = [Q|dO] MN-major
-            umma(col + 32, make_desc(da, true) + (uint64_t)(128 * k), make_desc(t1, true) + (uint64_t)(128 * k), id_dk, k);
+            umma(col + 32, dsm + po + (uint64_t)(128 * k), t1m + so + (uint64_t)(128 * k), id_dk, k);
 #pragma unroll
           for (int k = 0; k < 8; k++)   // [. | dV] = P^T [Q|dO]
-            umma(col + 64, make_desc(pa, true) + (uint64_t)(128 * k), make_desc(t1, true) + (uint64_t)(128 * k), id_dv, k);
+            umma(col + 64, pm + po + (uint64_t)(128 * k), t1m + so + (uint64_t)(128 * k), id_dv, k);
           umma_commit(&g_full[b]);
           umma_commit(&empty_in[st_j]);
         }
