@@ -129,6 +129,9 @@ class SelfDistillStep:
         self._warm = 0
         for p in self.teacher.parameters():
             p.requires_grad = False
+        # arena for the ACCUMULATED small gradients (LN affine, biases, rel-pos tables, patch embed): sized from the model
+        small = sum(p.numel() for p in self.student.parameters() if p.dim() == 1 or p.numel() <= (1 << 16))
+        self._arena_floats = 4 * small + (1 << 18)
         self._reducer = None
         if self.grad_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self._reducer = _GradReducer(list(self.student.parameters()))
@@ -143,7 +146,7 @@ class SelfDistillStep:
             self.opt.zero_grad()
         else:
             self.opt.zero_grad(set_to_none=True)
-        ops.begin_step(loss.device)  # one zero-filled arena for all small gradient accumulators of this backward
+        ops.begin_step(loss.device, self._arena_floats)  # one zero-filled arena for all small gradient accumulators
         try:
             loss.backward()
         finally:
@@ -184,11 +187,15 @@ class SelfDistillStep:
 
     # ---- CUDA-graph path ------------------------------------------------------------------------------------
     def _graphed(self, images: List[torch.Tensor], epoch: int) -> torch.Tensor:
-        if self._static_in is None:  # adopt the caller's tensors as the graph's static input buffers
-            self._static_in = list(images)
+        """Replay path.  The graph reads PRIVATE static input buffers (allocated on first use); every call copies the
+        caller's crops into them on the current stream, so the caller may recycle its own (prefetch) buffers freely.  A
+        batch of a different shape (e.g. a shorter last batch) runs the eager body instead."""
+        if self._static_in is None:
+            self._static_in = [torch.empty_like(im) for im in images]
+        if len(images) != len(self._static_in) or any(s.shape != im.shape for s, im in zip(self._static_in, images)):
+            return self._body(images, epoch)
         for s, im in zip(self._static_in, images):
-            if s.data_ptr() != im.data_ptr():
-                s.copy_(im, non_blocking=True)
+            s.copy_(im, non_blocking=True)
         if self._warm < 3:  # eager warm-up (allocator, cuBLAS workspaces, cached tables) before any capture
             self._warm += 1
             return self._body(self._static_in, epoch)

@@ -40,6 +40,7 @@ class _Arena:
     buf: Optional[Tensor] = None
     off = 0
     accs: Optional[dict] = None  # live only between begin_step() and end_step(): parameter -> its accumulator
+    warned = False
 
 
 def begin_step(device, nfloats: int = 1 << 22) -> None:
@@ -81,6 +82,11 @@ def _zeros(shape, device) -> Tensor:
         v = buf[_Arena.off:_Arena.off + n].view(*shape)
         _Arena.off += n16
         return v
+    if buf is not None and not _Arena.warned:
+        _Arena.warned = True
+        import warnings
+        warnings.warn("esvit_b200: gradient-accumulator arena exhausted (%d floats); falling back to per-tensor torch.zeros - "
+                      "pass a larger nfloats to ops.begin_step" % buf.numel())
     return torch.zeros(*shape, dtype=F32, device=device)
 
 

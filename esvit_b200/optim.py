@@ -50,9 +50,15 @@ class FusedAdamWEMA:
         self.state[:, 1] = self._base_flags.to(dev)
         self._flags_host = torch.empty(n, dtype=F32).pin_memory()
         self.hyper = torch.zeros(8, dtype=F32, device=dev)
-        self._hyper_host = torch.zeros(8, dtype=F32).pin_memory()
+        # ring of pinned staging buffers: the H2D copy of step N reads its buffer at EXECUTION time, while the host may
+        # already be preparing step N+k (no sync inside the step) - a single buffer would be overwritten in flight
+        self._hyper_ring = [torch.zeros(8, dtype=F32).pin_memory() for _ in range(8)]
+        self._hyper_events = [None] * 8
+        self._hyper_slot = 0
+        self._hyper_host = torch.zeros(8, dtype=F32)
         self._hyper_host[2], self._hyper_host[3], self._hyper_host[4] = betas[0], betas[1], eps
         self._hyper_host[7] = clip_grad if clip_grad else 0.0
+        self.betas, self.eps, self.clip_grad = tuple(betas), eps, clip_grad
         self.sumsq = torch.zeros(n, dtype=torch.float64, device=dev)
         # bf16 shadows of everything the GEMMs consume (Linear weights and biases); written by the sweep itself
         def wants_shadow(nm: str, p: torch.Tensor) -> bool:
@@ -83,7 +89,15 @@ class FusedAdamWEMA:
         h = self._hyper_host
         h[0], h[1] = lr, weight_decay
         h[5], h[6] = momentum, 1.0 - momentum  # float32(m), float32(1 - m) computed in double like the reference
-        self.hyper.copy_(h, non_blocking=True)
+        i = self._hyper_slot
+        self._hyper_slot = (i + 1) % len(self._hyper_ring)
+        ev = self._hyper_events[i]
+        if ev is not None:
+            ev.synchronize()  # the copy that last used this slot has executed (8 steps ago: never waits in practice)
+        self._hyper_ring[i].copy_(h)
+        self.hyper.copy_(self._hyper_ring[i], non_blocking=True)
+        ev = self._hyper_events[i] = ev if ev is not None else torch.cuda.Event()
+        ev.record()
 
     def set_skip_last_layer(self, skip: bool) -> None:
         """epoch < freeze_last_layer  <=>  the reference sets last_layer grads to None (utils.py:118-123)."""
@@ -124,12 +138,48 @@ class FusedAdamWEMA:
         """pre-clip per-tensor gradient norms of the last step (device tensor; what clip_gradients returned)."""
         return self.sumsq.sqrt().float()
 
-    def state_dict(self) -> Dict:
-        return {"names": self.names, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "state": self.state}
+    # ---- checkpoint interchange with the reference's `optimizer` entry (torch.optim.AdamW over utils.get_params_groups) ----
+    def _torch_order(self):
+        """indices of this optimiser's parameters in torch's numbering: group 0 = regularised, group 1 = biases / 1-D
+        (utils.py:672-683), trainable parameters only, each in named_parameters order"""
+        reg = [i for i, (nm, p) in enumerate(zip(self.names, self.params))
+               if not self.frozen[i] and not (nm.endswith(".bias") or p.dim() == 1)]
+        noreg = [i for i, (nm, p) in enumerate(zip(self.names, self.params))
+                 if not self.frozen[i] and (nm.endswith(".bias") or p.dim() == 1)]
+        return reg, noreg
 
-    def load_state_dict(self, sd: Dict) -> None:
-        for a, b in zip(self.exp_avg, sd["exp_avg"]):
-            a.copy_(b)
-        for a, b in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
-            a.copy_(b)
-        self.state.copy_(sd["state"])
+    def state_dict(self) -> Dict:
+        """torch.optim.AdamW layout: state[idx] = {step, exp_avg, exp_avg_sq} (clones) + the two param_groups, so the
+        reference's restart_from_checkpoint / a plain torch AdamW can load it."""
+        reg, noreg = self._torch_order()
+        h = self._hyper_host
+        state = {}
+        for k, i in enumerate(reg + noreg):
+            state[k] = {"step": self.state[i, 0].detach().clone().cpu(), "exp_avg": self.exp_avg[i].detach().clone(),
+                        "exp_avg_sq": self.exp_avg_sq[i].detach().clone()}
+        common = dict(lr=float(h[0]), betas=self.betas, eps=self.eps, amsgrad=False, maximize=False, foreach=None,
+                      capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True)
+        groups = [dict(common, weight_decay=float(h[1]), params=list(range(len(reg)))),
+                  dict(common, weight_decay=0.0, params=list(range(len(reg), len(reg) + len(noreg))))]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: Dict, **kwargs) -> None:
+        """accepts the torch AdamW layout (reference checkpoints) and this class's round-1 private layout"""
+        if "exp_avg" in sd:  # round-1 private format
+            for a, b in zip(self.exp_avg, sd["exp_avg"]):
+                a.copy_(b)
+            for a, b in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
+                a.copy_(b)
+            self.state.copy_(sd["state"])
+            return
+        reg, noreg = self._torch_order()
+        order = reg + noreg
+        for k, st in sd["state"].items():
+            i = order[int(k)]
+            self.exp_avg[i].copy_(st["exp_avg"])
+            self.exp_avg_sq[i].copy_(st["exp_avg_sq"])
+            self.state[i, 0] = float(st["step"])
+        g = sd.get("param_groups")
+        if g:
+            self._hyper_host[0] = g[0].get("lr", float(self._hyper_host[0]))
+            self._hyper_host[1] = g[0].get("weight_decay", float(self._hyper_host[1]))

@@ -529,3 +529,45 @@ def test_fused_adamw_clip_ema_matches_reference_sequence(misaligned):
             assert_close(a, b, 2e-6, f"teacher {n} step {it}")
         for k0, k1, q in zip(t_before, t.parameters(), s.parameters()):  # EMA bit-exact w.r.t. OUR updated student
             assert torch.equal(k1, k0.mul_(mom).add_((1 - mom) * q.detach()))
+
+
+def test_fused_optimizer_state_dict_interchanges_with_torch_adamw():
+    """FusedAdamWEMA.state_dict() uses torch.optim.AdamW's layout over utils.get_params_groups (what the reference saves as
+    `optimizer` in its checkpoints, main_esvit.py:476-488): a torch AdamW loads it, and it loads a torch AdamW's."""
+    import torch.nn as nn
+
+    from esvit_b200 import utils
+    from esvit_b200.optim import FusedAdamWEMA
+
+    class Toy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(16, 24)
+            self.norm = nn.LayerNorm(24)
+            self.last_layer = nn.Linear(24, 40, bias=False)
+            self.g = nn.Parameter(torch.ones(40, 1), requires_grad=False)
+
+    torch.manual_seed(3)
+    d = _dev()
+    s, t = Toy().to(d), Toy().to(d)
+    fopt = FusedAdamWEMA(s, t, clip_grad=3.0)
+    fopt.set_hyper(1e-3, 0.04, 0.996)
+    fopt.set_skip_last_layer(False)
+    for p_ in s.parameters():
+        p_.grad = torch.randn_like(p_) if p_.requires_grad else None
+    fopt.step()
+    sd = fopt.state_dict()
+    topt = torch.optim.AdamW(utils.get_params_groups(s))
+    topt.load_state_dict(sd)  # the reference's restart_from_checkpoint does exactly this
+    tparams = [p_ for g_ in topt.param_groups for p_ in g_["params"]]
+    reg, noreg = fopt._torch_order()
+    for k, i in enumerate(reg + noreg):
+        assert tparams[k] is fopt.params[i]
+        assert torch.equal(topt.state[tparams[k]]["exp_avg"], fopt.exp_avg[i])
+        assert float(topt.state[tparams[k]]["step"]) == 1.0
+    # and back: a fresh fused optimiser resumes from the torch optimiser's state
+    f2 = FusedAdamWEMA(s, t, clip_grad=3.0)
+    f2.load_state_dict(topt.state_dict())
+    for a, b in zip(f2.exp_avg_sq, fopt.exp_avg_sq):
+        assert torch.equal(a, b)
+    assert torch.equal(f2.state[:, 0], fopt.state[:, 0])
