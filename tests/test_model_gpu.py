@@ -126,7 +126,12 @@ def test_multicrop_wrapper_equals_model_forward():
 
 
 def test_cuda_graph_step_equals_eager_step():
-    """The captured-and-replayed step computes what the eager step computes (same kernels, same order)."""
+    """The captured-and-replayed step computes what the eager step computes: same kernels, same order.  It is NOT
+    bit-equal, and cannot be: the small-parameter gradients (LN gamma / beta, Linear biases, rel-pos bias tables, patch
+    embedding) are reduced across CTAs with fp32 global atomics whose arrival order differs from launch to launch - two
+    EAGER runs differ from each other in the same way.  (The GEMM weight gradients and the center column sums are
+    bit-reproducible: fixed-order folds, asserted in test_gemm2_gpu.py / test_ops_gpu.py.)  Gate: 2e-3 after six optimiser
+    steps at lr ~5e-4 with gradient clipping, i.e. the atomic-order noise amplified through AdamW's 1/sqrt(v)."""
     G = load_golden()
     stepE, sE, tE, lE, crops, hp = _build(G, True)
     stepG, sG, tG, lG, _, _ = _build(G, True)
