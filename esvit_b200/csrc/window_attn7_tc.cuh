@@ -47,7 +47,9 @@ __device__ __forceinline__ uint64_t global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
   return t;
 }
-// bounded spin (~2 s): a mis-programmed pipeline traps instead of hanging the GPU
+// Bounded wait (~2 s: a mis-programmed pipeline traps instead of hanging the GPU).  The try_wait carries a suspend-time hint
+// and failed tries back off with nanosleep: up to ten of the CTA's thirteen warps are waiting at any time, and a hot spin
+// loop in each of them took more issue slots than the softmax itself (ncu: 400 try_wait iterations per window pair).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
@@ -55,13 +57,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(a), "r"(parity)
+        : "r"(a), "r"(parity), "r"(1000u)
         : "memory");
     if (done) return;
-    if ((it & 1023u) == 1023u) {
+    __nanosleep(it < 4 ? 20 : 100);
+    if ((it & 255u) == 255u) {
       const uint64_t t = global_ns();
       if (t0 == 0) t0 = t;
       else if (t - t0 > 2000000000ull) __trap();
@@ -197,18 +200,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
     }
     // token row of row kk of window pair `pair` (-1 padded slot, -2 no such slot) and its shift region; (bb, wy, wx) of the
     // pair's two windows are computed once per pair, not per row
+    // (image, window row, window column) of a window index, advanced INCREMENTALLY from pair to pair: the persistent loop
+    // strides by a constant number of windows, so the div / mod by run-time values happens once per kernel, not per pair
+    struct WinPos { int bb, wy, wx; };
     struct PairGeo { int bb[2], wy[2], wx[2]; bool ok[2]; };
-    auto pair_geo = [&](int pair) {
+    auto from_index = [&](int win) {
+      WinPos q;
+      q.wx = win % g.nWx;
+      const int t2 = win / g.nWx;
+      q.wy = t2 % g.nWy;
+      q.bb = t2 / g.nWy;
+      return q;
+    };
+    auto advance = [&](WinPos& q, const WinPos& sft) {
+      q.wx += sft.wx;
+      int cy = q.wx >= g.nWx ? 1 : 0;
+      q.wx -= cy ? g.nWx : 0;
+      q.wy += sft.wy + cy;
+      cy = q.wy >= g.nWy ? 1 : 0;
+      q.wy -= cy ? g.nWy : 0;
+      q.bb += sft.bb + cy;
+    };
+    const WinPos wstep = from_index(2 * (int)gridDim.y), wone = {0, 0, 1};
+    WinPos wcur = from_index(2 * (int)blockIdx.y), wpf = from_index(2 * ((int)blockIdx.y + NSTAGE * (int)gridDim.y));
+    auto pair_geo = [&](const WinPos& w0, int pair) {
       PairGeo pg;
-#pragma unroll
-      for (int w = 0; w < 2; w++) {
-        const int win = 2 * pair + w;
-        pg.ok[w] = win < nwin_total;
-        pg.wx[w] = win % g.nWx;
-        const int t2 = win / g.nWx;
-        pg.wy[w] = t2 % g.nWy;
-        pg.bb[w] = t2 / g.nWy;
-      }
+      WinPos w1 = w0;
+      advance(w1, wone);
+      pg.bb[0] = w0.bb; pg.wy[0] = w0.wy; pg.wx[0] = w0.wx; pg.ok[0] = 2 * pair < nwin_total;
+      pg.bb[1] = w1.bb; pg.wy[1] = w1.wy; pg.wx[1] = w1.wx; pg.ok[1] = 2 * pair + 1 < nwin_total;
       return pg;
     };
     auto slot = [&](const PairGeo& pg, int kk, int& tk, int& rd) {
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
         const uint32_t ph = (it / NSTAGE) & 1;
         const int pair = blockIdx.y + it * gridDim.y;
         if (it + NSTAGE < n_items && c16 < 3) {  // L2 prefetch of the pair NSTAGE ahead: its gather will hit L2, not DRAM
-          const PairGeo pf = pair_geo(pair + NSTAGE * gridDim.y);
+          const PairGeo pf = pair_geo(wpf, pair + NSTAGE * (int)gridDim.y);
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {
             int tk, rd;
@@ -248,7 +268,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
             if (tk >= 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
           }
         }
-        const PairGeo pg = pair_geo(pair);
+        const PairGeo pg = pair_geo(wcur, pair);
+        advance(wcur, wstep);
+        advance(wpf, wstep);
         mbar_wait(&empty_qkv[st_i], ph ^ 1);
         uint8_t* stq = stages + st_i * STAGE_B;
         uint8_t* stkv = stq + TILE_B;

@@ -152,18 +152,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       iy[kk] = i / WS;
       ix[kk] = i - iy[kk] * WS;
     }
+    // (image, window row, window column) of a window index, advanced INCREMENTALLY from pair to pair: the persistent loop
+    // strides by a constant number of windows, so the div / mod by run-time values happens once per kernel, not per pair
+    struct WinPos { int bb, wy, wx; };
     struct PairGeo { int bb[2], wy[2], wx[2]; bool ok[2]; };
-    auto pair_geo = [&](int pair) {
+    auto from_index = [&](int win) {
+      WinPos q;
+      q.wx = win % g.nWx;
+      const int t2 = win / g.nWx;
+      q.wy = t2 % g.nWy;
+      q.bb = t2 / g.nWy;
+      return q;
+    };
+    auto advance = [&](WinPos& q, const WinPos& sft) {
+      q.wx += sft.wx;
+      int cy = q.wx >= g.nWx ? 1 : 0;
+      q.wx -= cy ? g.nWx : 0;
+      q.wy += sft.wy + cy;
+      cy = q.wy >= g.nWy ? 1 : 0;
+      q.wy -= cy ? g.nWy : 0;
+      q.bb += sft.bb + cy;
+    };
+    const WinPos wstep = from_index(2 * (int)gridDim.y), wone = {0, 0, 1};
+    WinPos wcur = from_index(2 * (int)blockIdx.y), wpf = from_index(2 * ((int)blockIdx.y + NSTAGE * (int)gridDim.y));
+    auto pair_geo = [&](const WinPos& w0, int pair) {
       PairGeo pg;
-#pragma unroll
-      for (int w = 0; w < 2; w++) {
-        const int win = 2 * pair + w;
-        pg.ok[w] = win < nwin_total;
-        pg.wx[w] = win % g.nWx;
-        const int t2 = win / g.nWx;
-        pg.wy[w] = t2 % g.nWy;
-        pg.bb[w] = t2 / g.nWy;
-      }
+      WinPos w1 = w0;
+      advance(w1, wone);
+      pg.bb[0] = w0.bb; pg.wy[0] = w0.wy; pg.wx[0] = w0.wx; pg.ok[0] = 2 * pair < nwin_total;
+      pg.bb[1] = w1.bb; pg.wy[1] = w1.wy; pg.wx[1] = w1.wx; pg.ok[1] = 2 * pair + 1 < nwin_total;
       return pg;
     };
     auto slot = [&](const PairGeo& pg, int kk, int& tk, int& rd) {  // -1 padded slot, -2 no such slot
@@ -195,7 +212,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
         const uint32_t ph = (it / NSTAGE) & 1;
         const int pair = blockIdx.y + it * gridDim.y;
         if (it + NSTAGE < n_items) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
-          const PairGeo pf = pair_geo(pair + NSTAGE * gridDim.y);
+          const PairGeo pf = pair_geo(wpf, pair + NSTAGE * (int)gridDim.y);
 #pragma unroll
           for (int kk = 0; kk < 8; kk++) {
             int tk, rd;
@@ -209,7 +226,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
             }
           }
         }
-        const PairGeo pg = pair_geo(pair);
+        const PairGeo pg = pair_geo(wcur, pair);
+        advance(wcur, wstep);
+        advance(wpf, wstep);
         mbar_wait(&empty_in[st_i], ph ^ 1);
         uint8_t* t1 = stages + st_i * STAGE_B;   // [Q | dO]
         uint8_t* t2 = t1 + TILE_B;               // [K | V]
