@@ -45,8 +45,8 @@ SIGNATURES = {
     "esvit_weight_norm_fwd": [P, P, P, P, L, I, P],
     "esvit_weight_norm_bwd": [P, P, P, P, I, P, P, L, I, P],
     "esvit_row_lse": [P, P, F, P, L, I, P],
-    "esvit_dino_ce_fwd": [P, P, P, P, P, P, F, F, P, L, I, P],
-    "esvit_dino_ce_bwd": [P, P, P, P, P, P, P, P, F, F, P, L, I, P],
+    "esvit_dino_ce_fwd": [P, P, P, P, P, P, P, F, F, P, L, I, P],
+    "esvit_dino_ce_bwd": [P, P, P, P, P, P, P, P, P, F, F, P, L, I, P],
     "esvit_weighted_sum": [P, P, I, P, P],
     "esvit_colsum_workspace_rows": [],
     "esvit_colsum": [P, L, I, P, P, P],

@@ -85,8 +85,10 @@ __global__ void __launch_bounds__(LT) row_lse_kernel(const bf16* __restrict__ x,
 __global__ void __launch_bounds__(LT) dino_ce_fwd_kernel(
     const bf16* __restrict__ s, const bf16* __restrict__ t, const float* __restrict__ center,
     float* __restrict__ lse_s, const float* __restrict__ lse_t, const int* __restrict__ trow,
-    float inv_temp_t, float inv_tau_s, float* __restrict__ row_loss, int K) {
-  const long long r = blockIdx.x;
+    float inv_temp_t, float inv_tau_s, float* __restrict__ row_loss, int K, const int* __restrict__ order) {
+  // CTA -> row through `order` (image-major): the CTAs resident together then stream the SAME image's teacher rows, which
+  // stay in L2 across the ~3.5 student rows paired with each (row-major = crop-major order re-read them from DRAM)
+  const long long r = order ? order[blockIdx.x] : blockIdx.x;
   const int t0 = trow[2 * r], t1 = trow[2 * r + 1];
   const bf16x8* sr = reinterpret_cast<const bf16x8*>(s + r * K);
   const bf16x8* tr0 = t0 >= 0 ? reinterpret_cast<const bf16x8*>(t + (long long)t0 * K) : nullptr;
@@ -141,8 +143,8 @@ __global__ void __launch_bounds__(LT) dino_ce_bwd_kernel(
     const bf16* __restrict__ s, const bf16* __restrict__ t, const float* __restrict__ center,
     const float* __restrict__ lse_s, const float* __restrict__ lse_t, const int* __restrict__ trow,
     const float* __restrict__ w, const float* __restrict__ gscale, float inv_temp_t, float inv_tau_s,
-    bf16* __restrict__ ds, int K) {
-  const long long r = blockIdx.x;
+    bf16* __restrict__ ds, int K, const int* __restrict__ order) {
+  const long long r = order ? order[blockIdx.x] : blockIdx.x;
   const int t0 = trow[2 * r], t1 = trow[2 * r + 1];
   const bf16x8* sr = reinterpret_cast<const bf16x8*>(s + r * K);
   bf16x8* dr = reinterpret_cast<bf16x8*>(ds + r * K);
@@ -321,20 +323,20 @@ ESVIT_API int esvit_row_lse(const void* x, const float* center, float inv_temp, 
 }
 
 ESVIT_API int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, float* lse_s,
-                                const float* lse_t, const int* trow, float inv_temp_t, float inv_tau_s,
+                                const float* lse_t, const int* trow, const int* order, float inv_temp_t, float inv_tau_s,
                                 float* row_loss, long long R, int K, void* stream) {
   if (K % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
   dino_ce_fwd_kernel<<<(unsigned)R, LT, 0, (cudaStream_t)stream>>>((const bf16*)s, (const bf16*)t, center, lse_s, lse_t,
-                                                                   trow, inv_temp_t, inv_tau_s, row_loss, K);
+                                                                   trow, inv_temp_t, inv_tau_s, row_loss, K, order);
   ESVIT_LAUNCH_CHECK();
 }
 
 ESVIT_API int esvit_dino_ce_bwd(const void* s, const void* t, const float* center, const float* lse_s,
-                                const float* lse_t, const int* trow, const float* w, const float* gscale,
+                                const float* lse_t, const int* trow, const int* order, const float* w, const float* gscale,
                                 float inv_temp_t, float inv_tau_s, void* ds, long long R, int K, void* stream) {
   if (K % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
   dino_ce_bwd_kernel<<<(unsigned)R, LT, 0, (cudaStream_t)stream>>>((const bf16*)s, (const bf16*)t, center, lse_s, lse_t,
-                                                                   trow, w, gscale, inv_temp_t, inv_tau_s, (bf16*)ds, K);
+                                                                   trow, w, gscale, inv_temp_t, inv_tau_s, (bf16*)ds, K, order);
   ESVIT_LAUNCH_CHECK();
 }
 

@@ -54,6 +54,20 @@ class _CenteredLoss(nn.Module):
             self._tables[key] = (trow.to(torch.int32).contiguous().to(device), w.to(device))
         return self._tables[key]
 
+    def _order(self, B: int, groups, device) -> torch.Tensor:
+        """int32 permutation of the student rows, IMAGE-major: rows are stored (crop, image, token); CTA i of the CE kernels
+        works on row order[i], so the CTAs resident together share one image's teacher rows (L2 instead of DRAM re-reads).
+        groups = [(number of crops, tokens per crop)] in storage order."""
+        key = ("order", B, tuple(groups), str(device))
+        if key not in self._tables:
+            parts, base = [], 0
+            for ncr, T in groups:
+                idx = base + torch.arange(ncr * B * T).view(ncr, B, T)   # [crop, image, token] -> row
+                parts.append(idx.permute(1, 0, 2).reshape(B, ncr * T))    # per image: its rows of this group
+                base += ncr * B * T
+            self._tables[key] = (torch.cat(parts, 1).reshape(-1).to(torch.int32).contiguous().to(device), None)
+        return self._tables[key][0]
+
     @staticmethod
     def _as_bf16(t: torch.Tensor) -> torch.Tensor:
         return t if t.dtype == BF16 else t.to(BF16)
@@ -88,7 +102,8 @@ class DINOLoss(_CenteredLoss):
         trow, w = self._cls_tables(B, 1.0 / (n_terms * B), s.device)
         center = self._snapshot(self.center)
         lse_t = ops.row_lse(t, center, 1.0 / temp)
-        loss = ops.DinoCEFn.apply(s, t, center, lse_t, trow, w, 1.0 / temp, 1.0 / self.student_temp)
+        loss = ops.DinoCEFn.apply(s, t, center, lse_t, trow, w, 1.0 / temp, 1.0 / self.student_temp,
+                                  self._order(B, [(self.ncrops, 1)], s.device))
         self.update_center(t)
         return loss
 
@@ -130,7 +145,8 @@ class DDINOLoss(_CenteredLoss):
         # view-level term (0.5 * DINO)
         trow_c, w_c = self._cls_tables(B, 0.5 / (n_terms * B), s_cls.device)
         lse_tc = ops.row_lse(t_cls, center, inv_t)
-        loss_c = ops.DinoCEFn.apply(s_cls, t_cls, center, lse_tc, trow_c, w_c, inv_t, inv_s)
+        loss_c = ops.DinoCEFn.apply(s_cls, t_cls, center, lse_tc, trow_c, w_c, inv_t, inv_s,
+                                    self._order(B, [(self.ncrops, 1)], s_cls.device))
 
         # region-level term: cosine arg-max pairing then the same fused CE
         with torch.no_grad():
@@ -138,7 +154,9 @@ class DDINOLoss(_CenteredLoss):
             self.last_indices = idx
         w_r = self._region_weights(B, Tg, Tl, n_terms, s_reg.device)
         lse_tr = ops.row_lse(t_reg, center_grid, inv_t)
-        loss_r = ops.DinoCEFn.apply(s_reg, t_reg, center_grid, lse_tr, trow_r, w_r, inv_t, inv_s)
+        groups = [(2, Tg)] + ([(self.ncrops - 2, Tl)] if self.ncrops > 2 and Tl > 0 else [])
+        loss_r = ops.DinoCEFn.apply(s_reg, t_reg, center_grid, lse_tr, trow_r, w_r, inv_t, inv_s,
+                                    self._order(B, groups, s_reg.device))
 
         self.update_center(t_cls, t_reg)
         return loss_c + loss_r

@@ -761,32 +761,33 @@ class DinoCEFn(Function):
     s bf16 [R,K] (grad), t bf16 [Rt,K], center fp32 [K], trow int32 [R,2], w fp32 [R]."""
 
     @staticmethod
-    def forward(ctx, s, t, center, lse_t, trow, w, inv_temp_t: float, inv_tau_s: float):
+    def forward(ctx, s, t, center, lse_t, trow, w, inv_temp_t: float, inv_tau_s: float, order=None):
         s, t = _chk(s, BF16, "student logits"), _chk(t, BF16, "teacher logits")
         center, lse_t, w = _chk(center, F32, "center"), _chk(lse_t, F32, "lse_t"), _chk(w, F32, "w")
         trow = _chk(trow, torch.int32, "trow")
+        order = _chk(order, torch.int32, "order")
         R, K = s.shape
         lse_s = torch.empty(R, dtype=F32, device=s.device)  # written by the CE kernel itself (one pass over s)
         row_loss = torch.empty(R, dtype=F32, device=s.device)
-        _lib.call("esvit_dino_ce_fwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), inv_temp_t, inv_tau_s,
+        _lib.call("esvit_dino_ce_fwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(order), inv_temp_t, inv_tau_s,
                   _p(row_loss), R, K, _stream())
         loss = torch.empty((), dtype=F32, device=s.device)
         _lib.call("esvit_weighted_sum", _p(row_loss), _p(w), R, _p(loss), _stream())
-        ctx.save_for_backward(s, t, center, lse_s, lse_t, trow, w)
+        ctx.save_for_backward(s, t, center, lse_s, lse_t, trow, w, order)
         ctx.temps = (inv_temp_t, inv_tau_s)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        s, t, center, lse_s, lse_t, trow, w = ctx.saved_tensors
+        s, t, center, lse_s, lse_t, trow, w, order = ctx.saved_tensors
         inv_temp_t, inv_tau_s = ctx.temps
         R, K = s.shape
         gs = _chk(g.reshape(1).to(F32), F32, "g")
         ds = torch.empty_like(s)
-        _lib.call("esvit_dino_ce_bwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(w), _p(gs),
+        _lib.call("esvit_dino_ce_bwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(order), _p(w), _p(gs),
                   inv_temp_t, inv_tau_s, _p(ds), R, K, _stream())
-        return ds, None, None, None, None, None, None, None
+        return ds, None, None, None, None, None, None, None, None
 
 
 _colsum_ws = {}

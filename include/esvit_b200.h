@@ -133,14 +133,15 @@ int esvit_weight_norm_bwd(const float* v, const float* g, const float* norm, con
  * dino_ce_fwd: row_loss[r] = n_r*lse_s[r] - sum_j <softmax((t[trow[r][j]]-center)*inv_temp_t), s[r]*inv_tau_s>;
  *   lse_s[r] = LSE(s[r]*inv_tau_s) is an OUTPUT (computed in the same pass, kept for the backward)
  * dino_ce_bwd: ds[r] = gscale[0]*w[r]*inv_tau_s * (n_r*softmax(s[r]*inv_tau_s) - sum_j q_j)   (bf16 out)
- * trow int32 [R,2], -1 = no pair.  s/t bf16 [R,K]/[Rt,K], K % 8 == 0. */
+ * trow int32 [R,2], -1 = no pair.  s/t bf16 [R,K]/[Rt,K], K % 8 == 0.
+ * order int32 [R] or NULL: CTA i works on row order[i] (a permutation; image-major keeps the paired teacher rows in L2). */
 int esvit_row_lse(const void* x, const float* center, float inv_temp, float* lse, long long R, int K, void* stream);
 int esvit_dino_ce_fwd(const void* s, const void* t, const float* center, float* lse_s, const float* lse_t,
-                      const int* trow, float inv_temp_t, float inv_tau_s, float* row_loss, long long R, int K,
-                      void* stream);
+                      const int* trow, const int* order, float inv_temp_t, float inv_tau_s, float* row_loss, long long R,
+                      int K, void* stream);
 int esvit_dino_ce_bwd(const void* s, const void* t, const float* center, const float* lse_s, const float* lse_t,
-                      const int* trow, const float* w, const float* gscale, float inv_temp_t, float inv_tau_s, void* ds,
-                      long long R, int K, void* stream);
+                      const int* trow, const int* order, const float* w, const float* gscale, float inv_temp_t,
+                      float inv_tau_s, void* ds, long long R, int K, void* stream);
 int esvit_weighted_sum(const float* v, const float* w, int R, float* out, void* stream);
 
 /* ---- update_center ----------------------------------------------------------- main_esvit.py:650-660, :752-770

@@ -6,7 +6,7 @@ CASES=${@:-"gemm_fwd_qkv0 gemm_gelu_fc1_0 gemm_mul_fc2dgrad_0 gemm_wgrad_qkv0 ge
 python scripts/ncu_kernels.py --list > gpurun_out/ncu_cases.json
 for c in $CASES; do
   k=$(python -c "import json;print(json.load(open('gpurun_out/ncu_cases.json'))['$c']['kernel'])")
-  s=2; case $c in dino_ce_*) s=5;; esac
+  s=2; case $c in dino_ce_fwd) s=5;; dino_ce_bwd) s=4;; esac   # the region-row launch (the cls launch runs beside it)
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -f -o gpurun_out/k_$c python scripts/ncu_kernels.py $c > gpurun_out/k_$c.log 2>&1
   # gpurun brings back at most 64 MiB: keep the raw-metric CSV of every capture, the .ncu-rep only for KEEP_REPS
   ncu -i gpurun_out/k_$c.ncu-rep --page raw --csv > gpurun_out/k_$c.csv 2>/dev/null
