@@ -89,3 +89,25 @@ def test_group_geometry_of_the_concatenated_layout():
         merged.append((B, (H + 1) // 2, (W + 1) // 2, row0))
         row0 += B * ((H + 1) // 2) * ((W + 1) // 2)
     assert merged == [(2, 28, 28, 0), (3, 12, 12, 2 * 28 * 28)]
+
+
+def test_loss_row_order_is_an_image_major_permutation():
+    """losses._order: the CTA -> student-row map of the CE kernels is a permutation of the (crop, image, token) storage
+    order that visits all rows of image 0, then image 1, ... (so the CTAs resident together share teacher rows)."""
+    from esvit_b200.losses import DDINOLoss
+    B, ncrops, Tg, Tl = 3, 5, 4, 2
+    m = DDINOLoss(64, ncrops, 0.04, 0.04, 0, 10)
+    o = m._order(B, [(2, Tg), (ncrops - 2, Tl)], "cpu").tolist()
+    R = B * (2 * Tg + (ncrops - 2) * Tl)
+    assert sorted(o) == list(range(R))
+
+    def image_of(r):
+        if r < 2 * B * Tg:
+            return (r // Tg) % B
+        return ((r - 2 * B * Tg) // Tl) % B
+    imgs = [image_of(r) for r in o]
+    assert imgs == sorted(imgs)                      # image-major
+    per = 2 * Tg + (ncrops - 2) * Tl
+    assert all(imgs[i * per] == i for i in range(B))
+    oc = m._order(B, [(ncrops, 1)], "cpu").tolist()  # cls rows: (crop, image) -> (image, crop)
+    assert oc == [v * B + b for b in range(B) for v in range(ncrops)]
