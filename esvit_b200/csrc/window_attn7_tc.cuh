@@ -19,6 +19,7 @@
 // K blocks overlap in a shared zero region.  Same math as window_attn_fwd7_kernel (log2-domain scores, P normalised in
 // fp32 then rounded to bf16, natural-log LSE saved for the backward).
 #pragma once
+#include <cuda.h>
 #include "wa_common.cuh"
 
 namespace wa {
@@ -117,6 +118,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+
+// ---- output through bulk tensor stores ---------------------------------------------------------------------------------
+// One (window, tensor) box of an output: 49 slots x 32 channels, staged in shared memory (64-byte rows, 64B swizzle) and
+// written by ONE bulk tensor store: rows of padded slots fall outside the [B, H, W, ch] tensor and are clipped.  A window
+// that wraps around the image (last window row / column of a shifted block) is staged as 2 or 4 dense sub-boxes, one per
+// wrapped copy, each with its own store and box shape: [7 - shift | shift] columns x [7 - shift | shift] rows (a store whose
+// box STARTS at a negative coordinate raises an illegal-instruction error on sm_100, measured; only the upper bound is
+// clipped).  Per-thread 16-byte stores of token rows, the alternative, cost four times the rest of the pair's work: the LSU
+// handles one 128-byte line per request and such an instruction touches 32 lines.
+struct OutMaps { CUtensorMap m[9]; };   // box (32 ch, bx, by, 1): m[iy * 3 + ix], bx / by in {7, 7 - shift, shift}
+constexpr int OBOX_B = 3584;            // 49 * 64 = 3136, rounded up to the 512-byte period of the swizzle
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(map),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// row of slot (siy, six) inside its window's staged box; xw / yw: the window wraps around the image in x / in y
+__device__ __forceinline__ int obox_row(int siy, int six, bool xw, bool yw, int shift) {
+  const int n1 = 7 - shift;
+  const int sx = xw && six >= n1, sy = yw && siy >= n1;
+  const int bw = xw ? (sx ? shift : n1) : 7, bh = yw ? (sy ? shift : n1) : 7;
+  return sy * n1 * 7 + sx * n1 * bh + (siy - (sy ? n1 : 0)) * bw + (six - (sx ? n1 : 0));
+}
+// the stores of window `win`'s staged box at shared address src (channel offset ch0): 1, 2 or 4 of them, one bulk group
+template <bool SHIFT>
+__device__ __forceinline__ void obox_store(const OutMaps& om, uint32_t src, int ch0, int win, const Geo& g) {
+  const int n1 = 7 - g.shift;
+  const int wx = win % g.nWx, t2 = win / g.nWx;
+  const int wy = t2 % g.nWy, bb = t2 / g.nWy;
+  const int x0 = wx * 7 + g.shift, y0 = wy * 7 + g.shift;   // x0 < Wp, y0 < Hp
+  const int xw = SHIFT && wx == g.nWx - 1, yw = SHIFT && wy == g.nWy - 1;
+  for (int sy = 0; sy <= yw; sy++)
+    for (int sx = 0; sx <= xw; sx++) {
+      const int bh = yw ? (sy ? g.shift : n1) : 7;
+      const int srow = sy * n1 * 7 + sx * n1 * bh;
+      tma_store_4d(&om.m[(yw ? 1 + sy : 0) * 3 + (xw ? 1 + sx : 0)], src + srow * 64, ch0, sx ? 0 : x0, sy ? 0 : y0, bb);
+    }
+}
+
 struct Smem {
   // byte offsets from the 1024-aligned base
   static constexpr int STAGES = 0;                               // [NSTAGE][Q | KV]
@@ -131,7 +171,8 @@ static size_t fwd7_tc_smem() { return (size_t)Smem::TOTAL + 1024; }
 template <bool SHIFT>
 __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
     const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
-    bf16* __restrict__ out, float* __restrict__ lse, Geo g, float scale, int nwin_total) {
+    bf16* __restrict__ out, float* __restrict__ lse, Geo g, float scale, int nwin_total,
+    const __grid_constant__ OutMaps om) {
   constexpr int WS = 7, NT = 49;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -244,6 +285,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
           const int ay = (ry >= g.Hp - WS) + (ry >= g.Hp - g.shift);
           const int ax = (rx >= g.Wp - WS) + (rx >= g.Wp - g.shift);
           rd = ay * 3 + ax;
+          // windows that wrap around the image in x / in y (flags for the row threads' output staging; the same for every
+          // slot of a window, so the region comparisons are unaffected)
+          if (pg.wx[w] == g.nWx - 1) rd |= 16;
+          if (pg.wy[w] == g.nWy - 1) rd |= 32;
         }
       }
     };
@@ -345,6 +390,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
     const float c = scale * LOG2E;
     const float* brow = bias_s + i * BIAS_LD;
     uint8_t* prow = pbuf + quad * P_B + w * 8192 + r * 128;
+    uint8_t* obox = pbuf + quad * P_B + w * OBOX_B;   // this window's output box: in data half 0 of the quad's P tile
+    const int siy = i / WS, six = i - siy * WS;
+    const bool issuer = lane == 0 && qw < 2;          // issues the bulk tensor stores of window qw of each pair
     for (int it = quad; it < n_items; it += 2) {
       const int st_i = it % NSTAGE;
       const uint32_t ph = (it >> 1) & 1;
@@ -393,7 +441,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
       const float s = (s0 + s1) + (s2 + s3);
       const float inv = __fdividef(1.f, s);
       // normalised P (fp32 -> bf16, as the reference under autocast) into this window's diagonal block of the A-operand tile
-      // (the quad's previous P V has completed: its o_full was awaited in the previous iteration's epilogue)
+      // (the quad's previous P V has completed: its o_full was awaited in the previous iteration's epilogue; the bulk stores
+      // of its output, staged in the same tile, have finished reading: awaited by the issuing threads before the barrier)
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      asm volatile("bar.sync %0, 128;\n" ::"r"(quad + 1) : "memory");
 #pragma unroll
       for (int ch = 0; ch < 8; ch++) {
         float p8[8];
@@ -415,17 +466,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[quad]);
-      if (tok >= 0) {
-        bf16* dst = out + (long long)tok * g.C + h * HD;
+      if (i < NT) {
+        const int orow = SHIFT ? obox_row(siy, six, (rid_r & 16) != 0, (rid_r & 32) != 0, g.shift) : i;
+        uint8_t* dst = obox + orow * 64;
+        const int sw = (orow >> 1) & 3;
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) {
           float f8[8];
 #pragma unroll
           for (int e = 0; e < 8; e++) f8[e] = __uint_as_float(o[ch * 8 + e]);
-          *reinterpret_cast<bf16x8*>(dst + ch * 8) = pack8(f8);
+          *reinterpret_cast<bf16x8*>(dst + ((ch ^ sw) * 16)) = pack8(f8);
         }
       }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      asm volatile("bar.sync %0, 128;\n" ::"r"(quad + 1) : "memory");
+      if (issuer) {
+        const int win2 = 2 * pair + qw;
+        if (win2 < nwin_total) obox_store<SHIFT>(om, smem_u32(pbuf + quad * P_B + qw * OBOX_B), h * HD, win2, g);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();

@@ -16,8 +16,11 @@
 // blocks / M atoms overlap in a shared zero region).
 // Gradients of the small parameters stay in this kernel: the rel-pos-bias gradient is accumulated in registers per row
 // thread over all windows (flushed through shared-memory bins once per CTA), the qkv-bias gradient = column sums of
-// dQ / dK / dV by a 31-shuffle butterfly per warp and tensor, accumulated in one register per lane.
+// dQ / dK / dV by a 16-shuffle butterfly per warp and tensor, accumulated in one register per lane.
+// TWO threads serve each row (16 row warps): the exp2 / dS arithmetic of a pair is the critical path of the pipeline, the
+// tensor-core work is not, so the row work is spread over twice the issue slots of the one-thread-per-row version.
 #pragma once
+#include <cstdio>
 #include "wa_common.cuh"
 #include "window_attn7_tc.cuh"
 
@@ -34,6 +37,10 @@ using tc::tmem_ld32;
 using tc::tmem_ld_wait;
 using tc::umma;
 using tc::umma_commit;
+using tc::OBOX_B;
+using tc::OutMaps;
+using tc::obox_row;
+using tc::obox_store;
 
 constexpr int ROWS = 128;
 constexpr int TILE_B = ROWS * 128;        // 16 KB
@@ -42,7 +49,8 @@ constexpr int NSTAGE = 3;
 constexpr int GDEPTH = 2;               // a pair's copies are awaited GDEPTH pairs after they were issued
 constexpr int PD_B = 3 * 8192;            // block-diagonal P or dS: [data0 | zero | data1]
 constexpr int BIAS_LD = 68;
-constexpr int NTHREADS = 32 * 11;         // warps 0-7 rows (2 quads), 8-9 gather, 10 MMA
+constexpr int GATHER_WARP = 16;           // warps 0-15 rows (2 quads x 8), 16 .. 16+NGW-1 gather, 16+NGW MMA
+constexpr int nthreads(int ngw) { return 32 * (GATHER_WARP + ngw + 1); }
 constexpr int TMEM_COLS = 512;
 constexpr int BUF_COLS = 256;             // per quad: S 128 + dP 128, re-used as dQ 32 | dK 32 | dV 64
 
@@ -58,17 +66,18 @@ struct Smem {
   static constexpr int BIAS = PD + 2 * 2 * PD_B;                 // [64][68] fp32
   static constexpr int BINS = BIAS + 64 * BIAS_LD * 4;           // [169 + 3] fp32 rel-pos-bias gradient bins
   static constexpr int META = BINS + 176 * 4;                    // tok [3][128] int, rid [3][128] int
-  static constexpr int BARS = META + 2 * NSTAGE * ROWS * 4;
+  static constexpr int DPART = META + 2 * NSTAGE * ROWS * 4;     // [2 quads][2 halves][128] fp32 partial rowsum(dO o O)
+  static constexpr int BARS = DPART + 4 * ROWS * 4;
   static constexpr int TOTAL = BARS + 256;
 };
 static size_t bwd7_tc_smem() { return (size_t)Smem::TOTAL + 1024; }
 
-// column sums of a [32 rows (lanes)] x [32 columns (v[0..31])] tile: after the butterfly lane l holds the sum of column
-// bitrev5(l)... the mapping is irrelevant as long as the flush uses the same one: lane l ends with column col_of_lane(l).
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-  // step s: partners differ in bit s of the lane id; the lane with bit = 0 keeps the lower half of the live columns
+// column sums of a [32 rows (lanes)] x [16 columns (v[0..15])] tile by a butterfly: at step `half` the lane whose bit `half`
+// is set keeps the upper half of the live columns, so after four steps lane l holds the sum of column (l & 15) over the 16
+// lanes that share bit 4 with it; one more exchange adds the other 16 rows.  16 shuffles per tensor.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 #pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
+  for (int half = 8; half >= 1; half >>= 1) {
     const bool upper = (lane & half) != 0;
 #pragma unroll
     for (int j = 0; j < half; j++) {
@@ -77,18 +86,38 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
       v[j] = mine + __shfl_xor_sync(0xffffffffu, send, half);
     }
   }
-  return v[0];
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
-// the column whose sum lane l holds after warp_colsum32: bit `half` of the lane selects the upper half at that step
-__device__ __forceinline__ int colsum_col_of_lane(int lane) { return lane & 31; }
+// byte offset (within a quad's [P | dS] region) of output box idx = window * 3 + tensor: the data halves of the P tile and
+// the first data half of the dS tile are free once the dQ / dK / dV GEMMs have completed (the shared zero regions are not
+// touched)
+__device__ __forceinline__ int obox_offset(int idx) {
+  const int reg = idx >> 1;
+  return (reg == 0 ? 0 : (reg == 1 ? 16384 : PD_B)) + (idx & 1) * OBOX_B;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 
-template <bool SHIFT>
-__global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
+// PROF: per-role cycle accounting (ESVIT_ATTN_PROF=1): lane 0 of one warp per role charges the time since its previous tick
+// to a named bucket; CTA (0, 0) prints the buckets at the end.  Development aid, not used by the product path.
+#define WA_TICK(slot) do { if (PROF) { const long long t__ = clock64(); pacc[slot] += t__ - tlast; tlast = t__; } } while (0)
+
+template <bool SHIFT, int NGW, bool PROF = false>
+__global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
     const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
-    int nwin_total) {
+    int nwin_total, int dbg, const __grid_constant__ OutMaps om) {
+  // dbg: 1 no L2 prefetch;  PROF builds only (results are then WRONG): 2 no dq/dk/dv stores, 4 no O / dO loads, 8 no copies
   constexpr int WS = 7, NT = 49, NB = 169;
+  constexpr int NTHREADS = nthreads(NGW), MMA_WARP = GATHER_WARP + NGW;
+  constexpr int RSTEP = 8 * NGW, RPT = (ROWS + RSTEP - 1) / RSTEP;   // gather: rows r = (t >> 2) + RSTEP kk < 128, kk < RPT
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = base + Smem::STAGES;
@@ -97,14 +126,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
   float* bins = reinterpret_cast<float*>(base + Smem::BINS);
   int* tokb = reinterpret_cast<int*>(base + Smem::META);
   int* ridb = tokb + NSTAGE * ROWS;
+  float* dpart = reinterpret_cast<float*>(base + Smem::DPART);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + Smem::BARS);
   uint64_t* full_in = bars;         // [3] count 64  (gather threads)
   uint64_t* empty_in = bars + 3;    // [3] count 1   (MMA commit after the second GEMM group)
   uint64_t* s_full = bars + 6;      // [2] count 1   (S and dP complete)
-  uint64_t* s_free = bars + 8;      // [2] count 4   (row warps have loaded S / dP)
-  uint64_t* pd_full = bars + 10;    // [2] count 4   (P and dS tiles written)
+  uint64_t* pd_full = bars + 10;    // [2] count 8   (P and dS tiles written; S / dP consumed)
   uint64_t* g_full = bars + 12;     // [2] count 1   (dQ / dK / dV complete)
-  uint64_t* g_free = bars + 14;     // [2] count 4   (row warps have loaded dQ / dK / dV: the accumulator columns are free)
+  uint64_t* g_free = bars + 14;     // [2] count 8   (row warps have loaded dQ / dK / dV: the accumulator columns are free)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int h = blockIdx.x;
@@ -121,13 +150,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
   }
   for (int i = threadIdx.x; i < 176; i += NTHREADS) bins[i] = 0.f;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_in[i], 64); mbar_init(&empty_in[i], 1); }
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_in[i], 32 * NGW); mbar_init(&empty_in[i], 1); }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&pd_full[i], 4); mbar_init(&g_full[i], 1); mbar_init(&g_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&pd_full[i], 8); mbar_init(&g_full[i], 1); mbar_init(&g_free[i], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 10) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
@@ -136,19 +165,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = PROF ? clock64() : 0;
 
-  if (warp == 8 || warp == 9) {
+  if (warp >= GATHER_WARP && warp < MMA_WARP) {
     // ===================== gather warps: 64 threads, 4 lanes per 64-byte segment, 8 rows per thread =====================
-    const int t = threadIdx.x - 256;
+    const int t = threadIdx.x - GATHER_WARP * 32;
     const int c16 = t & 3;
     uint4 bchunk[3];
 #pragma unroll
     for (int part = 0; part < 3; part++)
       bchunk[part] = __ldg(reinterpret_cast<const uint4*>(qkv_bias + part * g.C + h * HD + c16 * 8));
-    int iy[8], ix[8];   // slot geometry of this thread's 8 rows r = (t >> 2) + 16 kk (the same for every pair)
+    int iy[RPT], ix[RPT];   // slot geometry of this thread's rows (the same for every pair)
 #pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-      const int i = ((t >> 2) + 16 * kk) & 63;
+    for (int kk = 0; kk < RPT; kk++) {
+      const int i = ((t >> 2) + RSTEP * kk) & 63;
       iy[kk] = i / WS;
       ix[kk] = i - iy[kk] * WS;
     }
@@ -184,9 +215,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       return pg;
     };
     auto slot = [&](const PairGeo& pg, int kk, int& tk, int& rd) {  // -1 padded slot, -2 no such slot
-      const int w = kk >> 2;  // rows 16 kk + (t >> 2): kk < 4 -> window 0, else window 1
+      const int rr = (t >> 2) + RSTEP * kk;
+      const int w = (rr >> 6) & 1;
       tk = -2; rd = 0;
-      if (pg.ok[w] && iy[kk] < WS) {
+      if (rr < ROWS && pg.ok[w] && iy[kk] < WS) {
         const int ry = pg.wy[w] * WS + iy[kk], rx = pg.wx[w] * WS + ix[kk];
         int py = ry + g.shift, px = rx + g.shift;
         if (py >= g.Hp) py -= g.Hp;
@@ -196,25 +228,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
           const int ay = (ry >= g.Hp - WS) + (ry >= g.Hp - g.shift);
           const int ax = (rx >= g.Wp - WS) + (rx >= g.Wp - g.shift);
           rd = ay * 3 + ax;
+          // windows that wrap around the image in x / in y (flags for the row threads' output staging; the same for every
+          // slot of a window, so the region comparisons are unaffected)
+          if (pg.wx[w] == g.nWx - 1) rd |= 16;
+          if (pg.wy[w] == g.nWy - 1) rd |= 32;
         }
       }
     };
     for (int it = 0; it < n_items + GDEPTH; it++) {
       // FIRST publish the pair issued GDEPTH iterations ago (its copies have landed), THEN wait for a free stage: the stage
       // this iteration needs is released by GEMMs that themselves wait for that publication (circular otherwise)
+      WA_TICK(0);
       if (it >= GDEPTH) {
         cp_async_wait<GDEPTH - 1>();
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         mbar_arrive(&full_in[(it - GDEPTH) % NSTAGE]);
       }
+      WA_TICK(1);
       if (it < n_items) {
         const int st_i = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
         const int pair = blockIdx.y + it * gridDim.y;
-        if (it + NSTAGE < n_items) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
+        if (it + NSTAGE < n_items && !(dbg & 1)) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
           const PairGeo pf = pair_geo(wpf, pair + NSTAGE * (int)gridDim.y);
 #pragma unroll
-          for (int kk = 0; kk < 8; kk++) {
+          for (int kk = 0; kk < RPT; kk++) {
             int tk, rd;
             slot(pf, kk, tk, rd);
             if (tk >= 0) {
@@ -229,12 +267,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
         const PairGeo pg = pair_geo(wcur, pair);
         advance(wcur, wstep);
         advance(wpf, wstep);
+        WA_TICK(2);
         mbar_wait(&empty_in[st_i], ph ^ 1);
+        WA_TICK(3);
         uint8_t* t1 = stages + st_i * STAGE_B;   // [Q | dO]
         uint8_t* t2 = t1 + TILE_B;               // [K | V]
 #pragma unroll
-        for (int kk = 0; kk < 8; kk++) {
-          const int r = (t >> 2) + 16 * kk;
+        for (int kk = 0; kk < RPT; kk++) {
+          const int r = (t >> 2) + RSTEP * kk;
+          if (ROWS % RSTEP != 0 && r >= ROWS) break;
           int tk, rd;
           slot(pg, kk, tk, rd);
           const int sw = r & 7;
@@ -242,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
           uint8_t* dd = t1 + r * 128 + (((4 + c16) ^ sw) * 16);
           uint8_t* dk = t2 + r * 128 + ((c16 ^ sw) * 16);
           uint8_t* dv = t2 + r * 128 + (((4 + c16) ^ sw) * 16);
+          if (PROF && (dbg & 8) && it > 0) tk = -2;
           if (tk == -1) {          // padded slot: q / k / v = the qkv bias, its output row is cropped away: dO = 0
             *reinterpret_cast<uint4*>(dq) = bchunk[0];
             *reinterpret_cast<uint4*>(dk) = bchunk[1];
@@ -264,7 +306,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       }
       cp_async_commit();
     }
-  } else if (warp == 10) {
+    WA_TICK(0);
+    if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == GATHER_WARP * 32)
+      printf("bwd7_tc gather: items %d | copy-issue %lld  cp.async.wait %lld  prefetch+geometry %lld  wait empty_in %lld\n", n_items,
+             pacc[0], pacc[1], pacc[2], pacc[3]);
+  } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t id_s = make_idesc2(128, 128, false, false);
@@ -279,8 +325,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       for (int it = 0; it <= n_items; it++) {
         if (it < n_items) {  // S(it), dP(it)
           const int b = it & 1, st_i = it % NSTAGE;
+          WA_TICK(0);
           mbar_wait(&full_in[st_i], (it / NSTAGE) & 1);
+          WA_TICK(1);
           mbar_wait(&g_free[b], ((it >> 1) & 1) ^ 1);   // the quad has drained dQ / dK / dV of its previous pair
+          WA_TICK(2);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint64_t so = (uint64_t)(st_i * (STAGE_B >> 4));
 #pragma unroll
@@ -292,7 +341,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
         if (it > 0) {        // dQ, dK, dV of pair it-1
           const int j = it - 1, b = j & 1, st_j = j % NSTAGE;
           const uint32_t ph = (j >> 1) & 1;
+          WA_TICK(0);
           mbar_wait(&pd_full[b], ph);                   // implies the quad has loaded S / dP: their columns are free
+          WA_TICK(3);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint64_t so = (uint64_t)(st_j * (STAGE_B >> 4)), po = (uint64_t)(b * ((2 * PD_B) >> 4));
           const uint32_t col = tmem_base + b * BUF_COLS;
@@ -309,61 +360,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
           umma_commit(&empty_in[st_j]);
         }
       }
+      WA_TICK(0);
+      if (PROF && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("bwd7_tc mma: issue %lld  wait full_in %lld  wait g_free %lld  wait pd_full %lld\n", pacc[0], pacc[1], pacc[2], pacc[3]);
     }
   } else {
-    // ===================== row warps: two quads, thread = row (query row in phase 1, q / k / v row in phase 2) =========
-    const int quad = warp >> 2, qw = warp & 3;
-    const int r = qw * 32 + lane;
+    // ===================== row warps: two quads of EIGHT warps, TWO threads per row =====================
+    // warp = quad * 8 + half * 4 + lq: lq = the TMEM lane quarter (warp id % 4), half = which 32 of the row's 64 key columns
+    // (phase 1) / which 16 of the 32 channels (phase 2) the thread owns.
+    const int quad = warp >> 3, hh = (warp >> 2) & 1, lq = warp & 3;
+    const int r = lq * 32 + lane;
     const int w = r >> 6, i = r & 63;
-    const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + quad * BUF_COLS;
+    const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + quad * BUF_COLS;
     const float c = scale * LOG2E;
-    const float* brow = bias_s + i * BIAS_LD;
-    uint8_t* prow = pdbuf + quad * 2 * PD_B + w * 8192 + r * 128;   // P row; dS row at + PD_B
-    float dsacc[64];
+    const float* brow = bias_s + i * BIAS_LD + hh * 32;
+    uint8_t* obase = pdbuf + quad * 2 * PD_B;                      // the quad's [P | dS] region, re-used for the output boxes
+    uint8_t* prow = obase + w * 8192 + r * 128;                     // P row; dS row at + PD_B
+    float* dmine = dpart + (quad * 2 + hh) * ROWS + r;
+    const float* dother = dpart + (quad * 2 + (hh ^ 1)) * ROWS + r;
+    const int siy = i / WS, six = i - siy * WS;
+    const bool issuer = lane == 0 && (warp & 7) < 6;   // issues the bulk tensor stores of one output box per pair
+    float dsacc[32];
 #pragma unroll
-    for (int j = 0; j < 64; j++) dsacc[j] = 0.f;
-    float csum[3] = {0.f, 0.f, 0.f};  // per-lane column-sum accumulators of dQ, dK, dV (column colsum_col_of_lane(lane))
+    for (int j = 0; j < 32; j++) dsacc[j] = 0.f;
+    float csum[3] = {0.f, 0.f, 0.f};  // per-lane column sums of dQ, dK, dV (channel hh * 16 + (lane & 15))
     for (int it = quad; it < n_items; it += 2) {
       const int st_i = it % NSTAGE;
       const uint32_t ph = (it >> 1) & 1;
       const int pair = blockIdx.y + it * gridDim.y;
+      WA_TICK(7);
       mbar_wait(&full_in[st_i], (it / NSTAGE) & 1);
+      WA_TICK(1);
       const int tok = tokb[st_i * ROWS + r];
       int rid_r = 0;
       if (SHIFT) rid_r = ridb[st_i * ROWS + r];
-      // D = rowsum(dO o O) and the row's LSE, straight from global memory (L2: prefetched by the gather warps)
-      float Dr = 0.f, l2 = INFINITY;  // rows that do not exist: P = exp2(-inf) = 0
-      if (tok >= 0) {
-        const uint4* po = reinterpret_cast<const uint4*>(out + (long long)tok * g.C + h * HD);
-        const uint4* pd = reinterpret_cast<const uint4*>(dout + (long long)tok * g.C + h * HD);
+      // D = rowsum(dO o O): this thread's 16 channels, the other half through shared memory.  The row's LSE.
+      // padded query rows (tok == -1) have dO = 0, hence dS = 0 and no dV contribution: P = exp2(-inf) = 0 serves them too
+      // (and keeps an undefined saved LSE of a skipped all-padding tile out of the arithmetic)
+      float Dr = 0.f, l2 = INFINITY;
+      if (tok >= 0 && !(PROF && (dbg & 4))) {
+        const uint4* po = reinterpret_cast<const uint4*>(out + (long long)tok * g.C + h * HD + hh * 16);
+        const uint4* pd = reinterpret_cast<const uint4*>(dout + (long long)tok * g.C + h * HD + hh * 16);
+        const uint4 uo0 = __ldg(po), uo1 = __ldg(po + 1), ud0 = __ldg(pd), ud1 = __ldg(pd + 1);
+        l2 = __ldg(lse + ((long long)(2 * pair + w) * g.nH + h) * NT + i) * LOG2E;
+        float fo[8], fd[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(&uo0), fo);
+        unpack8(*reinterpret_cast<const bf16x8*>(&ud0), fd);
 #pragma unroll
-        for (int ch = 0; ch < 4; ch++) {
-          float fo[8], fd[8];
-          const uint4 uo = __ldg(po + ch), ud = __ldg(pd + ch);
-          unpack8(*reinterpret_cast<const bf16x8*>(&uo), fo);
-          unpack8(*reinterpret_cast<const bf16x8*>(&ud), fd);
+        for (int e = 0; e < 8; e++) Dr = fmaf(fo[e], fd[e], Dr);
+        unpack8(*reinterpret_cast<const bf16x8*>(&uo1), fo);
+        unpack8(*reinterpret_cast<const bf16x8*>(&ud1), fd);
 #pragma unroll
-          for (int e = 0; e < 8; e++) Dr = fmaf(fo[e], fd[e], Dr);
-        }
+        for (int e = 0; e < 8; e++) Dr = fmaf(fo[e], fd[e], Dr);
       }
-      // padded query rows (tok == -1) have dO = 0, hence dS = 0 and no dV contribution: P = 0 serves them too (and keeps
-      // an undefined saved LSE of a skipped all-padding tile out of the arithmetic)
-      if (tok >= 0) l2 = __ldg(lse + ((long long)(2 * pair + w) * g.nH + h) * NT + i) * LOG2E;
+      *dmine = Dr;
+      WA_TICK(2);
       mbar_wait(&s_full[quad], ph);
+      WA_TICK(3);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // (the quad's bulk stores of the previous pair have finished READING the P / dS regions: awaited by the issuing
+      // threads before this barrier)
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      asm volatile("bar.sync %0, 256;\n" ::"r"(quad + 1) : "memory");
+      Dr += *dother;
+      WA_TICK(4);
       // the quad's previous dQ / dK / dV GEMMs have completed (g_full awaited below in the previous iteration), so the
       // P / dS tiles may be overwritten
 #pragma unroll
-      for (int hh = 0; hh < 2; hh++) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(taddr + w * 64 + hh * 32, sv);
-        tmem_ld32(taddr + 128 + w * 64 + hh * 32, dv);
+      for (int q16 = 0; q16 < 2; q16++) {
+        uint32_t sv[16], dv[16];
+        tmem_ld16(taddr + w * 64 + hh * 32 + q16 * 16, sv);
+        tmem_ld16(taddr + 128 + w * 64 + hh * 32 + q16 * 16, dv);
         tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ch++) {
+        for (int c2 = 0; c2 < 2; c2++) {
+          const int ch = q16 * 2 + c2;
           float p8[8], d8[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(brow + hh * 32 + ch * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(brow + hh * 32 + ch * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(brow + ch * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(brow + ch * 8 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           int rc[8];
           if (SHIFT) {
@@ -373,14 +447,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
           }
 #pragma unroll
           for (int e = 0; e < 8; e++) {
-            const int j = hh * 32 + ch * 8 + e;
-            float x = fmaf(__uint_as_float(sv[ch * 8 + e]), c, bb[e]) - l2;
-            if (SHIFT) { if (j < NT && rc[e] != rid_r) x += -100.f * LOG2E; }
+            const int jl = ch * 8 + e;          // column within this thread's half
+            float x = fmaf(__uint_as_float(sv[c2 * 8 + e]), c, bb[e]) - l2;
+            if (SHIFT) { if (hh * 32 + jl < NT && rc[e] != rid_r) x += -100.f * LOG2E; }
             const float pj = ex2(x);
-            const float dsj = pj * (__uint_as_float(dv[ch * 8 + e]) - Dr);
+            const float dsj = pj * (__uint_as_float(dv[c2 * 8 + e]) - Dr);
             p8[e] = pj;
             d8[e] = dsj;
-            dsacc[j] += dsj;
+            dsacc[jl] += dsj;
           }
           const int sw = ((hh * 4 + ch) ^ (r & 7)) * 16;
           *reinterpret_cast<bf16x8*>(prow + sw) = pack8(p8);
@@ -390,50 +464,73 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_bwd7_tc_kernel(
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&s_free[quad]); mbar_arrive(&pd_full[quad]); }
-      // phase 2: dQ / dK / dV of this pair -> bf16 -> token order; column sums -> qkv-bias gradient
+      if (lane == 0) mbar_arrive(&pd_full[quad]);
+      WA_TICK(5);
+      // phase 2: dQ / dK / dV of this pair -> bf16 -> token order; column sums -> qkv-bias gradient.  This thread: channels
+      // hh * 16 .. + 15 of its row in each tensor: dQ at +0, dK at +32, dV at +96 (columns 32..63 of [. | dV])
       mbar_wait(&g_full[quad], ph);
+      WA_TICK(6);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      // one tensor at a time (32 live values): dQ at +0, dK at +32, dV at +96 (columns 32..63 of [. | dV])
+      uint32_t gr[3][16];
+      tmem_ld16(taddr + hh * 16, gr[0]);
+      tmem_ld16(taddr + 32 + hh * 16, gr[1]);
+      tmem_ld16(taddr + 96 + hh * 16, gr[2]);
+      tmem_ld_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_free[quad]);   // the accumulator columns may be overwritten
+      WA_TICK(8);
+      // row of this slot inside its window's staged box.  A window that wraps around the image (last window row / column of
+      // a shifted block) is staged as 2 or 4 dense sub-boxes, one per wrapped copy: [n1 | shift] columns x [n1 | shift] rows
+      const int orow = SHIFT ? obox_row(siy, six, (rid_r & 16) != 0, (rid_r & 32) != 0, g.shift) : i;
 #pragma unroll
       for (int part = 0; part < 3; part++) {
-        uint32_t gr[32];
-        tmem_ld32(taddr + (part == 0 ? 0 : (part == 1 ? 32 : 96)), gr);
-        tmem_ld_wait();
-        if (part == 2) {  // all three accumulators are in registers / consumed: the columns may be overwritten
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&g_free[quad]);
-        }
-        float f[32];
+        float f[16];
         const float sc = part == 2 ? 1.f : scale;
 #pragma unroll
-        for (int e = 0; e < 32; e++) f[e] = __uint_as_float(gr[e]) * sc;
-        if (tok >= 0) {
-          bf16* dst = dqkv + (long long)tok * 3 * g.C + part * g.C + h * HD;
-#pragma unroll
-          for (int ch = 0; ch < 4; ch++) *reinterpret_cast<bf16x8*>(dst + ch * 8) = pack8(f + ch * 8);
+        for (int e = 0; e < 16; e++) f[e] = __uint_as_float(gr[part][e]) * sc;
+        if (i < NT) {   // this row's 32 bytes of box (w, part): chunks 2 hh, 2 hh + 1 of its 64-byte row
+          uint8_t* box = obase + obox_offset(w * 3 + part) + orow * 64;
+          const int sw = (orow >> 1) & 3;
+          *reinterpret_cast<bf16x8*>(box + (((2 * hh) ^ sw) * 16)) = pack8(f);
+          *reinterpret_cast<bf16x8*>(box + (((2 * hh + 1) ^ sw) * 16)) = pack8(f + 8);
         }
         // qkv-bias gradient: column sums over ALL slots of the window (padded ones included; missing rows are 0)
-        csum[part] += warp_colsum32(f, lane);
+        csum[part] += warp_colsum16(f, lane);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      WA_TICK(9);
+      asm volatile("bar.sync %0, 256;\n" ::"r"(quad + 1) : "memory");
+      WA_TICK(10);
+      // six issuing threads per quad (lane 0 of its first six warps), one per (window, tensor) box
+      if (issuer && !(PROF && (dbg & 2))) {
+        const int ww = (warp & 7) >= 3, part = (warp & 7) - 3 * ww;
+        const int win = 2 * pair + ww;
+        if (win < nwin_total) obox_store<SHIFT>(om, smem_u32(obase) + obox_offset(ww * 3 + part), part * g.C + h * HD, win, g);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
       }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    WA_TICK(7);
+    if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && ((threadIdx.x & 255) == 0 || (threadIdx.x & 255) == 160))
+      printf("bwd7_tc row quad %d warp %d: wait full_in %lld  O/dO/lse loads %lld  wait s_full %lld  D exchange %lld  phase 1 %lld  "
+             "wait g_full %lld | phase 2: tmem ld %lld  stage+colsum %lld  bar %lld  store issue+loop %lld\n", quad, warp & 7, pacc[1],
+             pacc[2], pacc[3], pacc[4], pacc[5], pacc[6], pacc[8], pacc[9], pacc[10], pacc[7]);
     // flush: rel-pos-bias gradient through the CTA's shared-memory bins, qkv-bias gradient straight to global memory
     if (i < NT) {
 #pragma unroll
-      for (int j = 0; j < 64; j++)
-        if (j < NT) atomicAdd(&bins[bias_index<WS>(i, j)], dsacc[j]);
+      for (int j = 0; j < 32; j++)
+        if (hh * 32 + j < NT) atomicAdd(&bins[bias_index<WS>(i, hh * 32 + j)], dsacc[j]);
     }
-    {
-      const int col = colsum_col_of_lane(lane);
+    if (lane < 16) {
 #pragma unroll
-      for (int part = 0; part < 3; part++) atomicAdd(&dqkv_bias[part * g.C + h * HD + col], csum[part]);
+      for (int part = 0; part < 3; part++) atomicAdd(&dqkv_bias[part * g.C + h * HD + hh * 16 + lane], csum[part]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   for (int i = threadIdx.x; i < NB; i += NTHREADS) atomicAdd(&dbias_table[i * g.nH + h], bins[i]);
-  if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
 }  // namespace tcb
