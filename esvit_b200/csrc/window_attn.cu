@@ -125,8 +125,8 @@ ESVIT_API int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const
   if (ws == 7) {
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
     if (!bias_ready) wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
-    static const int use_tc = [] { const char* e = getenv("ESVIT_ATTN_TC"); return e ? atoi(e) : 0; }();
-    if (use_tc && (shift == 0 || shift == 3)) {
+    static const int use_tc = [] { const char* e = getenv("ESVIT_ATTN_TC"); return e ? atoi(e) : 2; }();
+    if ((use_tc & 1) && (shift == 0 || shift == 3)) {   // ESVIT_ATTN_TC: bit 0 forward, bit 1 backward
       // tcgen05 / TMEM forward core: one persistent CTA per SM, head on blockIdx.x, pairs of windows on blockIdx.y
       const size_t smem_tc = wa::tc::fwd7_tc_smem();
       cudaError_t e = wa::opt_in_smem(wa::tc::window_attn_fwd7_tc_kernel<true>, smem_tc);
@@ -182,8 +182,8 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
   if (ws == 7) {
     if (!bias_ws) return ESVIT_ERR_BAD_ARG;
     if (!bias_ready) wa::expand_bias7_kernel<<<nH, 256, 0, st>>>(bias_table, bias_ws, nH);
-    static const int use_tc = [] { const char* ev = getenv("ESVIT_ATTN_TC"); return ev ? atoi(ev) : 0; }();
-    if (use_tc >= 2 && (shift == 0 || shift == 3)) {   // (sub-box offsets of the wrapped output parts: 128-byte aligned)
+    static const int use_tc = [] { const char* ev = getenv("ESVIT_ATTN_TC"); return ev ? atoi(ev) : 2; }();   // default: tcgen05
+    if ((use_tc & 2) && (shift == 0 || shift == 3)) {   // (sub-box offsets of the wrapped output parts: 128-byte aligned)
       // tcgen05 / TMEM backward core: one persistent CTA per SM, head on blockIdx.x, pairs of windows on blockIdx.y
       const size_t smem_tc = wa::tcb::bwd7_tc_smem();
       const int npairs = (nwin + 1) / 2;
@@ -196,28 +196,27 @@ ESVIT_API int esvit_window_attn_bwd(const void* qkv, const void* qkv_bias, const
       wa::tc::OutMaps tm_dqkv;
       if (!wa::make_out_maps(&tm_dqkv, dqkv, B, H, W, 3 * C, shift)) return ESVIT_ERR_BAD_ARG;
       static const int prof = [] { const char* ev = getenv("ESVIT_ATTN_PROF"); return ev ? atoi(ev) : 0; }();
-      static const int ngw = [] { const char* ev = getenv("ESVIT_ATTN_NGW"); return ev ? atoi(ev) : 3; }();  // 16 + 3 + 1 warps = 640 threads x 96 registers
+      static const int ngw = [] { const char* ev = getenv("ESVIT_ATTN_NGW"); return ev ? atoi(ev) : 21; }();  // 21: 2 gather + 1 MMA warp
       const char* de = getenv("ESVIT_ATTN_DBG");
-      const int dbg = de ? (prof ? atoi(de) : (atoi(de) & 1)) : 0;
-#define WA_TCB_LAUNCH(SH, NG, PR)                                                                                          \
+      const int dbg = de ? (prof ? atoi(de) : (atoi(de) & 65)) : 0;
+#define WA_TCB_LAUNCH(SH, NG, NM, PR)                                                                                      \
   do {                                                                                                                     \
-    auto kfn = wa::tcb::window_attn_bwd7_tc_kernel<SH, NG, PR>;                                                            \
+    auto kfn = wa::tcb::window_attn_bwd7_tc_kernel<SH, NG, NM, PR>;                                                        \
     cudaError_t e2 = wa::opt_in_smem(kfn, smem_tc);                                                                        \
     if (e2 != cudaSuccess) return (int)e2;                                                                                 \
-    kfn<<<dim3(nH, gy), wa::tcb::nthreads(NG), smem_tc, st>>>(q, qb, bias_ws, (const bf16*)out, (const bf16*)dout, lse,    \
-                                                              (bf16*)dqkv, dbias_table, dqkv_bias, g, scale, nwin, dbg,   \
-                                                              tm_dqkv);                                                   \
+    kfn<<<dim3(nH, gy), wa::tcb::nthreads(NG, NM), smem_tc, st>>>(q, qb, bias_ws, (const bf16*)out, (const bf16*)dout,     \
+                                                                  lse, (bf16*)dqkv, dbias_table, dqkv_bias, g, scale,     \
+                                                                  nwin, dbg, tm_dqkv);                                    \
   } while (0)
-      // prof: development aid (per-role cycle accounting printed by CTA (0, 0)); ngw: gather warps per CTA
+#define WA_TCB_SHIFT(NG, NM, PR) do { if (shift > 0) WA_TCB_LAUNCH(true, NG, NM, PR); else WA_TCB_LAUNCH(false, NG, NM, PR); } while (0)
+      // 20 warps (640 threads x 96 registers): 16 row warps + ngw gather warps + 1 or 2 MMA-issuing warps (ngw 2: one per
+      // quad).  prof: development aid (per-role cycle accounting printed by CTA (0, 0))
       if (prof) {
-        if (ngw == 2) { if (shift > 0) WA_TCB_LAUNCH(true, 2, true); else WA_TCB_LAUNCH(false, 2, true); }
-        else if (ngw == 3) { if (shift > 0) WA_TCB_LAUNCH(true, 3, true); else WA_TCB_LAUNCH(false, 3, true); }
-        else { if (shift > 0) WA_TCB_LAUNCH(true, 4, true); else WA_TCB_LAUNCH(false, 4, true); }
+        if (ngw == 2) WA_TCB_SHIFT(2, 2, true); else if (ngw == 21) WA_TCB_SHIFT(2, 1, true); else WA_TCB_SHIFT(3, 1, true);
       } else {
-        if (ngw == 2) { if (shift > 0) WA_TCB_LAUNCH(true, 2, false); else WA_TCB_LAUNCH(false, 2, false); }
-        else if (ngw == 3) { if (shift > 0) WA_TCB_LAUNCH(true, 3, false); else WA_TCB_LAUNCH(false, 3, false); }
-        else { if (shift > 0) WA_TCB_LAUNCH(true, 4, false); else WA_TCB_LAUNCH(false, 4, false); }
+        if (ngw == 2) WA_TCB_SHIFT(2, 2, false); else if (ngw == 21) WA_TCB_SHIFT(2, 1, false); else WA_TCB_SHIFT(3, 1, false);
       }
+#undef WA_TCB_SHIFT
 #undef WA_TCB_LAUNCH
       ESVIT_LAUNCH_CHECK();
     }

@@ -292,19 +292,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attn_fwd7_tc_kernel(
         }
       }
     };
-    for (int it = 0; it < n_items + GDEPTH; it++) {
+    const int gdepth = (g.dbg & 128) ? 1 : GDEPTH;   // (A/B knob: publish a pair one gather iteration after its copies)
+    for (int it = 0; it < n_items + gdepth; it++) {
       // FIRST publish the pair issued GDEPTH iterations ago (its copies have landed), THEN wait for a free stage: the stage
       // this iteration needs is released by MMAs that themselves wait for that publication (circular otherwise)
-      if (it >= GDEPTH) {
-        cp_async_wait<GDEPTH - 1>();
+      if (it >= gdepth) {
+        if (gdepth == 1) cp_async_wait<0>(); else cp_async_wait<GDEPTH - 1>();
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
-        mbar_arrive(&full_qkv[(it - GDEPTH) % NSTAGE]);
+        mbar_arrive(&full_qkv[(it - gdepth) % NSTAGE]);
       }
       if (it < n_items) {
         const int st_i = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
         const int pair = blockIdx.y + it * gridDim.y;
-        if (it + NSTAGE < n_items && c16 < 3) {  // L2 prefetch of the pair NSTAGE ahead: its gather will hit L2, not DRAM
+        if (it + NSTAGE < n_items && c16 < 3 && (g.dbg & 64)) {  // L2 prefetch of the pair NSTAGE ahead (ESVIT_ATTN_DBG=64;
+          // off: a prefetch instruction with 32 distinct lines costs the gather warp ~400 cycles, measured in the backward)
           const PairGeo pf = pair_geo(wpf, pair + NSTAGE * (int)gridDim.y);
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {

@@ -46,11 +46,12 @@ constexpr int ROWS = 128;
 constexpr int TILE_B = ROWS * 128;        // 16 KB
 constexpr int STAGE_B = 2 * TILE_B;       // [Q | dO] and [K | V]
 constexpr int NSTAGE = 3;
-constexpr int GDEPTH = 2;               // a pair's copies are awaited GDEPTH pairs after they were issued
+constexpr int GDEPTH = 1;               // a pair is published GDEPTH gather iterations after its copies were issued (2: the
+                                        // publication then sits behind the NEXT stage wait + copy issue, measured slower)
 constexpr int PD_B = 3 * 8192;            // block-diagonal P or dS: [data0 | zero | data1]
 constexpr int BIAS_LD = 68;
-constexpr int GATHER_WARP = 16;           // warps 0-15 rows (2 quads x 8), 16 .. 16+NGW-1 gather, 16+NGW MMA
-constexpr int nthreads(int ngw) { return 32 * (GATHER_WARP + ngw + 1); }
+constexpr int GATHER_WARP = 16;           // warps 0-15 rows (2 quads x 8), then NGW gather warps, then NMW MMA-issuing warps
+constexpr int nthreads(int ngw, int nmw) { return 32 * (GATHER_WARP + ngw + nmw); }
 constexpr int TMEM_COLS = 512;
 constexpr int BUF_COLS = 256;             // per quad: S 128 + dP 128, re-used as dQ 32 | dK 32 | dV 64
 
@@ -66,8 +67,8 @@ struct Smem {
   static constexpr int BIAS = PD + 2 * 2 * PD_B;                 // [64][68] fp32
   static constexpr int BINS = BIAS + 64 * BIAS_LD * 4;           // [169 + 3] fp32 rel-pos-bias gradient bins
   static constexpr int META = BINS + 176 * 4;                    // tok [3][128] int, rid [3][128] int
-  static constexpr int DPART = META + 2 * NSTAGE * ROWS * 4;     // [2 quads][2 halves][128] fp32 partial rowsum(dO o O)
-  static constexpr int BARS = DPART + 4 * ROWS * 4;
+  static constexpr int DPART = META + 2 * NSTAGE * ROWS * 4;     // [2 pairs in flight][2 quads][2 halves][128] fp32 partial rowsum(dO o O)
+  static constexpr int BARS = DPART + 8 * ROWS * 4;
   static constexpr int TOTAL = BARS + 256;
 };
 static size_t bwd7_tc_smem() { return (size_t)Smem::TOTAL + 1024; }
@@ -108,15 +109,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 // to a named bucket; CTA (0, 0) prints the buckets at the end.  Development aid, not used by the product path.
 #define WA_TICK(slot) do { if (PROF) { const long long t__ = clock64(); pacc[slot] += t__ - tlast; tlast = t__; } } while (0)
 
-template <bool SHIFT, int NGW, bool PROF = false>
-__global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
+template <bool SHIFT, int NGW, int NMW, bool PROF = false>
+__global__ void __launch_bounds__(nthreads(NGW, NMW), 1) window_attn_bwd7_tc_kernel(
     const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_bias, const float* __restrict__ bexp,
     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
     bf16* __restrict__ dqkv, float* __restrict__ dbias_table, float* __restrict__ dqkv_bias, Geo g, float scale,
     int nwin_total, int dbg, const __grid_constant__ OutMaps om) {
-  // dbg: 1 no L2 prefetch;  PROF builds only (results are then WRONG): 2 no dq/dk/dv stores, 4 no O / dO loads, 8 no copies
+  // dbg: 1 L2 prefetch of the O / dO rows by the gather warps (costs them ~400 cycles per prefetch instruction; off);  PROF builds only (results are then WRONG): 2 no dq/dk/dv stores, 4 no O / dO loads, 8 no copies
   constexpr int WS = 7, NT = 49, NB = 169;
-  constexpr int NTHREADS = nthreads(NGW), MMA_WARP = GATHER_WARP + NGW;
+  constexpr int NTHREADS = nthreads(NGW, NMW), MMA_WARP = GATHER_WARP + NGW;
   constexpr int RSTEP = 8 * NGW, RPT = (ROWS + RSTEP - 1) / RSTEP;   // gather: rows r = (t >> 2) + RSTEP kk < 128, kk < RPT
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
   uint64_t* pd_full = bars + 10;    // [2] count 8   (P and dS tiles written; S / dP consumed)
   uint64_t* g_full = bars + 12;     // [2] count 1   (dQ / dK / dV complete)
   uint64_t* g_free = bars + 14;     // [2] count 8   (row warps have loaded dQ / dK / dV: the accumulator columns are free)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* meta_full = bars + 16;  // [3] count 32 NGW (tok / rid of the stage written: published when the copies are ISSUED)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int h = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
   }
   for (int i = threadIdx.x; i < 176; i += NTHREADS) bins[i] = 0.f;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_in[i], 32 * NGW); mbar_init(&empty_in[i], 1); }
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_in[i], 32 * NGW); mbar_init(&empty_in[i], 1); mbar_init(&meta_full[i], 32 * NGW); }
     for (int i = 0; i < 2; i++) {
       mbar_init(&s_full[i], 1); mbar_init(&pd_full[i], 8); mbar_init(&g_full[i], 1); mbar_init(&g_free[i], 8);
     }
@@ -249,17 +251,18 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
         const int st_i = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
         const int pair = blockIdx.y + it * gridDim.y;
-        if (it + NSTAGE < n_items && !(dbg & 1)) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
+        if (it + NSTAGE < n_items && (dbg & 1)) {  // L2 prefetch of the pair three ahead (q / k / v segments, dO and O rows)
           const PairGeo pf = pair_geo(wpf, pair + NSTAGE * (int)gridDim.y);
 #pragma unroll
           for (int kk = 0; kk < RPT; kk++) {
             int tk, rd;
             slot(pf, kk, tk, rd);
-            if (tk >= 0) {
-              if (c16 < 3) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + c16 * g.C + h * HD));
-              else {
-                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dout + (long long)tk * g.C + h * HD));
-                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(out + (long long)tk * g.C + h * HD));
+            if (tk >= 0) {   // the rows the row threads read straight from global memory; dbg & 64: the q / k / v segments too
+              if (c16 == 0) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(dout + (long long)tk * g.C + h * HD));
+              else if (c16 == 1) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(out + (long long)tk * g.C + h * HD));
+              else if (dbg & 64) {
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + (c16 - 2) * g.C + h * HD));
+                if (c16 == 3) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qkv + (long long)tk * 3 * g.C + 2 * g.C + h * HD));
               }
             }
           }
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
             ridb[st_i * ROWS + r] = rd;
           }
         }
+        mbar_arrive(&meta_full[st_i]);   // the row threads fetch their per-row global data one pair ahead of the tiles
       }
       cp_async_commit();
     }
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
     if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == GATHER_WARP * 32)
       printf("bwd7_tc gather: items %d | copy-issue %lld  cp.async.wait %lld  prefetch+geometry %lld  wait empty_in %lld\n", n_items,
              pacc[0], pacc[1], pacc[2], pacc[3]);
-  } else if (warp == MMA_WARP) {
+  } else if (warp >= MMA_WARP) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t id_s = make_idesc2(128, 128, false, false);
@@ -322,46 +326,58 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
       const uint64_t t1k = make_desc(s0, false), t2k = make_desc(s0 + TILE_B, false);      // [Q|dO], [K|V] K-major
       const uint64_t t1m = make_desc(s0, true), t2m = make_desc(s0 + TILE_B, true);        // ... MN-major
       const uint64_t pm = make_desc(p0, true), dsk = make_desc(p0 + PD_B, false), dsm = make_desc(p0 + PD_B, true);
-      for (int it = 0; it <= n_items; it++) {
-        if (it < n_items) {  // S(it), dP(it)
-          const int b = it & 1, st_i = it % NSTAGE;
-          WA_TICK(0);
-          mbar_wait(&full_in[st_i], (it / NSTAGE) & 1);
-          WA_TICK(1);
-          mbar_wait(&g_free[b], ((it >> 1) & 1) ^ 1);   // the quad has drained dQ / dK / dV of its previous pair
-          WA_TICK(2);
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint64_t so = (uint64_t)(st_i * (STAGE_B >> 4));
+      auto issue_s = [&](int it) {   // S(it), dP(it)
+        const int b = it & 1, st_i = it % NSTAGE;
+        WA_TICK(0);
+        mbar_wait(&full_in[st_i], (it / NSTAGE) & 1);
+        WA_TICK(1);
+        mbar_wait(&g_free[b], ((it >> 1) & 1) ^ 1);   // the quad has drained dQ / dK / dV of its previous pair
+        WA_TICK(2);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint64_t so = (uint64_t)(st_i * (STAGE_B >> 4));
 #pragma unroll
-          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, t1k + so + 2 * k, t2k + so + 2 * k, id_s, k);                 // Q K^T
+        for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS, t1k + so + 2 * k, t2k + so + 2 * k, id_s, k);                 // Q K^T
 #pragma unroll
-          for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS + 128, t1k + so + 4 + 2 * k, t2k + so + 4 + 2 * k, id_s, k);   // dO V^T
-          umma_commit(&s_full[b]);
+        for (int k = 0; k < 2; k++) umma(tmem_base + b * BUF_COLS + 128, t1k + so + 4 + 2 * k, t2k + so + 4 + 2 * k, id_s, k);   // dO V^T
+        umma_commit(&s_full[b]);
+      };
+      auto issue_g = [&](int j) {    // dQ, dK, dV of pair j
+        const int b = j & 1, st_j = j % NSTAGE;
+        const uint32_t ph = (j >> 1) & 1;
+        WA_TICK(0);
+        mbar_wait(&pd_full[b], ph);                   // implies the quad has loaded S / dP: their columns are free
+        WA_TICK(3);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint64_t so = (uint64_t)(st_j * (STAGE_B >> 4)), po = (uint64_t)(b * ((2 * PD_B) >> 4));
+        const uint32_t col = tmem_base + b * BUF_COLS;
+#pragma unroll
+        for (int k = 0; k < 8; k++)   // dQ = dS K : A K-major (K block k>>2 at +8 KB), B = [K|V] MN-major rows 16k..
+          umma(col, dsk + po + (uint64_t)((k >> 2) * (8192 >> 4) + 2 * (k & 3)), t2m + so + (uint64_t)(128 * k), id_dq, k);
+#pragma unroll
+        for (int k = 0; k < 8; k++)   // dK = dS^T Q : A = dS MN-major (query rows 16k..), B = [Q|dO] MN-major
+          umma(col + 32, dsm + po + (uint64_t)(128 * k), t1m + so + (uint64_t)(128 * k), id_dk, k);
+#pragma unroll
+        for (int k = 0; k < 8; k++)   // [. | dV] = P^T [Q|dO]
+          umma(col + 64, pm + po + (uint64_t)(128 * k), t1m + so + (uint64_t)(128 * k), id_dv, k);
+        umma_commit(&g_full[b]);
+        umma_commit(&empty_in[st_j]);
+      };
+      if (NMW == 1) {
+        // one issuing thread: S / dP of pair it, then dQ / dK / dV of pair it - 1 (the other quad's)
+        for (int it = 0; it <= n_items; it++) {
+          if (it < n_items) issue_s(it);
+          if (it > 0) issue_g(it - 1);
         }
-        if (it > 0) {        // dQ, dK, dV of pair it-1
-          const int j = it - 1, b = j & 1, st_j = j % NSTAGE;
-          const uint32_t ph = (j >> 1) & 1;
-          WA_TICK(0);
-          mbar_wait(&pd_full[b], ph);                   // implies the quad has loaded S / dP: their columns are free
-          WA_TICK(3);
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint64_t so = (uint64_t)(st_j * (STAGE_B >> 4)), po = (uint64_t)(b * ((2 * PD_B) >> 4));
-          const uint32_t col = tmem_base + b * BUF_COLS;
-#pragma unroll
-          for (int k = 0; k < 8; k++)   // dQ = dS K : A K-major (K block k>>2 at +8 KB), B = [K|V] MN-major rows 16k..
-            umma(col, dsk + po + (uint64_t)((k >> 2) * (8192 >> 4) + 2 * (k & 3)), t2m + so + (uint64_t)(128 * k), id_dq, k);
-#pragma unroll
-          for (int k = 0; k < 8; k++)   // dK = dS^T Q : A = dS MN-major (query rows 16k..), B = [Q|dO] MN-major
-            umma(col + 32, dsm + po + (uint64_t)(128 * k), t1m + so + (uint64_t)(128 * k), id_dk, k);
-#pragma unroll
-          for (int k = 0; k < 8; k++)   // [. | dV] = P^T [Q|dO]
-            umma(col + 64, pm + po + (uint64_t)(128 * k), t1m + so + (uint64_t)(128 * k), id_dv, k);
-          umma_commit(&g_full[b]);
-          umma_commit(&empty_in[st_j]);
+      } else {
+        // one issuing thread PER QUAD: a quad that is late (its accumulators not drained, its P / dS not written) does not
+        // hold up the other quad's GEMMs behind it in a single thread's program order
+        for (int it = warp - MMA_WARP; it < n_items; it += 2) {
+          issue_s(it);
+          issue_g(it);
         }
       }
       WA_TICK(0);
-      if (PROF && blockIdx.x == 0 && blockIdx.y == 0)
+      if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && warp == MMA_WARP)
         printf("bwd7_tc mma: issue %lld  wait full_in %lld  wait g_free %lld  wait pd_full %lld\n", pacc[0], pacc[1], pacc[2], pacc[3]);
     }
   } else {
@@ -376,33 +392,31 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
     const float* brow = bias_s + i * BIAS_LD + hh * 32;
     uint8_t* obase = pdbuf + quad * 2 * PD_B;                      // the quad's [P | dS] region, re-used for the output boxes
     uint8_t* prow = obase + w * 8192 + r * 128;                     // P row; dS row at + PD_B
-    float* dmine = dpart + (quad * 2 + hh) * ROWS + r;
-    const float* dother = dpart + (quad * 2 + (hh ^ 1)) * ROWS + r;
     const int siy = i / WS, six = i - siy * WS;
     const bool issuer = lane == 0 && (warp & 7) < 6;   // issues the bulk tensor stores of one output box per pair
     float dsacc[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) dsacc[j] = 0.f;
     float csum[3] = {0.f, 0.f, 0.f};  // per-lane column sums of dQ, dK, dV (channel hh * 16 + (lane & 15))
-    for (int it = quad; it < n_items; it += 2) {
-      const int st_i = it % NSTAGE;
-      const uint32_t ph = (it >> 1) & 1;
-      const int pair = blockIdx.y + it * gridDim.y;
+    // what a pair needs from global memory per row, fetched one pair of this quad AHEAD (while the quad waits for the
+    // dQ / dK / dV GEMMs of the current pair; the L2 round trip was 20 % of the quad's time when it sat at the top of the
+    // iteration): D = rowsum(dO o O) -- this thread's 16 channels, left in shared memory for the exchange with the row's
+    // other thread -- and the row's LSE.  Padded query rows (tok == -1) have dO = 0, hence dS = 0 and no dV contribution:
+    // P = exp2(-inf) = 0 serves them too (and keeps an undefined saved LSE of a skipped all-padding tile out of the arithmetic)
+    auto prep = [&](int it2, int& rid_o, float& l2_o) {
+      const int st2 = it2 % NSTAGE;
       WA_TICK(7);
-      mbar_wait(&full_in[st_i], (it / NSTAGE) & 1);
+      mbar_wait(&meta_full[st2], (it2 / NSTAGE) & 1);
       WA_TICK(1);
-      const int tok = tokb[st_i * ROWS + r];
-      int rid_r = 0;
-      if (SHIFT) rid_r = ridb[st_i * ROWS + r];
-      // D = rowsum(dO o O): this thread's 16 channels, the other half through shared memory.  The row's LSE.
-      // padded query rows (tok == -1) have dO = 0, hence dS = 0 and no dV contribution: P = exp2(-inf) = 0 serves them too
-      // (and keeps an undefined saved LSE of a skipped all-padding tile out of the arithmetic)
+      const int tok = tokb[st2 * ROWS + r];
+      rid_o = SHIFT ? ridb[st2 * ROWS + r] : 0;
       float Dr = 0.f, l2 = INFINITY;
       if (tok >= 0 && !(PROF && (dbg & 4))) {
+        const int pair2 = blockIdx.y + it2 * gridDim.y;
         const uint4* po = reinterpret_cast<const uint4*>(out + (long long)tok * g.C + h * HD + hh * 16);
         const uint4* pd = reinterpret_cast<const uint4*>(dout + (long long)tok * g.C + h * HD + hh * 16);
         const uint4 uo0 = __ldg(po), uo1 = __ldg(po + 1), ud0 = __ldg(pd), ud1 = __ldg(pd + 1);
-        l2 = __ldg(lse + ((long long)(2 * pair + w) * g.nH + h) * NT + i) * LOG2E;
+        l2 = __ldg(lse + ((long long)(2 * pair2 + w) * g.nH + h) * NT + i) * LOG2E;
         float fo[8], fd[8];
         unpack8(*reinterpret_cast<const bf16x8*>(&uo0), fo);
         unpack8(*reinterpret_cast<const bf16x8*>(&ud0), fd);
@@ -413,8 +427,18 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
 #pragma unroll
         for (int e = 0; e < 8; e++) Dr = fmaf(fo[e], fd[e], Dr);
       }
-      *dmine = Dr;
+      dpart[((((it2 >> 1) & 1) * 2 + quad) * 2 + hh) * ROWS + r] = Dr;
+      l2_o = l2;
       WA_TICK(2);
+    };
+    int rid_r = 0;
+    float l2 = INFINITY;
+    if (quad < n_items) prep(quad, rid_r, l2);
+    for (int it = quad; it < n_items; it += 2) {
+      const int st_i = it % NSTAGE;
+      const uint32_t ph = (it >> 1) & 1;
+      const int pair = blockIdx.y + it * gridDim.y;
+      const float* dbuf = dpart + (((it >> 1) & 1) * 2 + quad) * 2 * ROWS + r;
       mbar_wait(&s_full[quad], ph);
       WA_TICK(3);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -422,7 +446,7 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
       // threads before this barrier)
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
       asm volatile("bar.sync %0, 256;\n" ::"r"(quad + 1) : "memory");
-      Dr += *dother;
+      const float Dr = dbuf[0] + dbuf[ROWS];
       WA_TICK(4);
       // the quad's previous dQ / dK / dV GEMMs have completed (g_full awaited below in the previous iteration), so the
       // P / dS tiles may be overwritten
@@ -466,6 +490,9 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
       __syncwarp();
       if (lane == 0) mbar_arrive(&pd_full[quad]);
       WA_TICK(5);
+      int rid_n = 0;
+      float l2_n = INFINITY;
+      if (it + 2 < n_items) prep(it + 2, rid_n, l2_n);
       // phase 2: dQ / dK / dV of this pair -> bf16 -> token order; column sums -> qkv-bias gradient.  This thread: channels
       // hh * 16 .. + 15 of its row in each tensor: dQ at +0, dK at +32, dV at +96 (columns 32..63 of [. | dV])
       mbar_wait(&g_full[quad], ph);
@@ -509,11 +536,13 @@ __global__ void __launch_bounds__(nthreads(NGW), 1) window_attn_bwd7_tc_kernel(
         if (win < nwin_total) obox_store<SHIFT>(om, smem_u32(obase) + obox_offset(ww * 3 + part), part * g.C + h * HD, win, g);
         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
       }
+      rid_r = rid_n;
+      l2 = l2_n;
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     WA_TICK(7);
     if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && ((threadIdx.x & 255) == 0 || (threadIdx.x & 255) == 160))
-      printf("bwd7_tc row quad %d warp %d: wait full_in %lld  O/dO/lse loads %lld  wait s_full %lld  D exchange %lld  phase 1 %lld  "
+      printf("bwd7_tc row quad %d warp %d: wait meta %lld  O/dO/lse loads %lld  wait s_full %lld  D exchange %lld  phase 1 %lld  "
              "wait g_full %lld | phase 2: tmem ld %lld  stage+colsum %lld  bar %lld  store issue+loop %lld\n", quad, warp & 7, pacc[1],
              pacc[2], pacc[3], pacc[4], pacc[5], pacc[6], pacc[8], pacc[9], pacc[10], pacc[7]);
     // flush: rel-pos-bias gradient through the CTA's shared-memory bins, qkv-bias gradient straight to global memory
