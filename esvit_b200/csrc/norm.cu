@@ -5,6 +5,7 @@
 //   x = shortcut + drop_path(branch); y = norm(x)          :329-331 with :283 of the next block
 //   PatchMerging: 2x2 gather-concat -> LN(4C)               :393-417
 //   final norm + AdaptiveAvgPool1d                          :687-689
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -104,10 +105,10 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(
 }
 
 // backward: G = dxo + LNbwd(dy) ; dx = G ; ddelta = keep * G ; dgamma += dy*xhat ; dbeta += dy ; ddbias += keep*G
-template <int LPR, int NV, typename DyT>
-// NV <= 3 (C <= 384 at 8/16/32 lanes per row: every stage-0..2 launch, 85 % of this kernel's bytes): 3 CTAs/SM at 80
-// registers (32 bytes of spill) instead of 2 at 128 - the kernel is latency-bound on bytes in flight, not on ALU
-__global__ void __launch_bounds__(NV <= 4 ? 256 : 128, NV <= 3 ? 3 : 1) add_ln_bwd_kernel(
+template <int LPR, int NV, typename DyT, int OCC>
+// NV <= 3 (C <= 384 at 8/16/32 lanes per row: every stage-0..2 launch, 85 % of this kernel's bytes): OCC = 3 CTAs/SM at 80
+// registers (some spill) or 2 at 128 - the kernel is latency-bound on bytes in flight, not on ALU (ESVIT_ADDLN_OCC)
+__global__ void __launch_bounds__(NV <= 4 ? 256 : 128, NV <= 3 ? OCC : 1) add_ln_bwd_kernel(
     const DyT* __restrict__ dy, const float* __restrict__ dxo, const float* __restrict__ xs,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
     const float* __restrict__ keep, int tokens_per_sample, float* __restrict__ dx, bf16* __restrict__ ddelta,
@@ -129,7 +130,15 @@ __global__ void __launch_bounds__(NV <= 4 ? 256 : 128, NV <= 3 ? 3 : 1) add_ln_b
     const long long row = r0 + sub;
     const bool ok = row < T;
     const float ks = (keep && ok) ? keep[row / tokens_per_sample] : 1.f;
-    float4 G[NV];
+    // every global load of the row is issued before the first use (the incoming gradient of the residual stream too: it
+    // used to be loaded after the two row reductions, a second exposed round trip per iteration of a latency-bound kernel)
+    float4 G[NV], o[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int c = (i * LPR + l) * 4;
+      o[i] = make_float4(0, 0, 0, 0);
+      if (dxo && ok && c < C) o[i] = Vec4IO<float>::ld(dxo + row * C + c);
+    }
     if (dy) {
       const float mean = ok ? mean_i[row] : 0.f, rstd = ok ? rstd_i[row] : 0.f;
       float4 xh[NV], g[NV];
@@ -155,23 +164,19 @@ __global__ void __launch_bounds__(NV <= 4 ? 256 : 128, NV <= 3 ? 3 : 1) add_ln_b
       s2 = group_sum<LPR>(s2) * invC;
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        G[i].x = rstd * (g[i].x - s1 - xh[i].x * s2);
-        G[i].y = rstd * (g[i].y - s1 - xh[i].y * s2);
-        G[i].z = rstd * (g[i].z - s1 - xh[i].z * s2);
-        G[i].w = rstd * (g[i].w - s1 - xh[i].w * s2);
+        G[i].x = fmaf(rstd, g[i].x - s1 - xh[i].x * s2, o[i].x);
+        G[i].y = fmaf(rstd, g[i].y - s1 - xh[i].y * s2, o[i].y);
+        G[i].z = fmaf(rstd, g[i].z - s1 - xh[i].z * s2, o[i].z);
+        G[i].w = fmaf(rstd, g[i].w - s1 - xh[i].w * s2, o[i].w);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; i++) G[i] = make_float4(0, 0, 0, 0);
+      for (int i = 0; i < NV; i++) G[i] = o[i];
     }
 #pragma unroll
     for (int i = 0; i < NV; i++) {
       const int c = (i * LPR + l) * 4;
       if (ok && c < C) {
-        if (dxo) {
-          float4 o = Vec4IO<float>::ld(dxo + row * C + c);
-          G[i].x += o.x; G[i].y += o.y; G[i].z += o.z; G[i].w += o.w;
-        }
         if (dx) Vec4IO<float>::st(dx + row * C + c, G[i]);
         if (ddelta)
           Vec4IO<bf16>::st(ddelta + row * C + c, make_float4(ks * G[i].x, ks * G[i].y, ks * G[i].z, ks * G[i].w));
@@ -423,20 +428,25 @@ ESVIT_API int esvit_add_ln_bwd(const void* dy, int dy_is_bf16, const float* dxo,
   const long long warp_rows = (T + 32 / lpr - 1) / (32 / lpr);
   // every CTA ends with 3*C global atomics: keep the CTA count modest
   // persistent grid = resident CTAs x small integer (no partial last wave)
-  const int grid = row_grid(warp_rows, threads / 32, nv <= 3 ? 3 : (threads == 256 ? 4 : 8));
+  static const int occ = [] { const char* ev = getenv("ESVIT_ADDLN_OCC"); return ev && atoi(ev) == 3 ? 3 : 2; }();   // 2 (no spills) measured 0.68 of HBM over a step, 3: 0.66
+  const int grid = row_grid(warp_rows, threads / 32, nv <= 3 ? occ : (threads == 256 ? 4 : 8));
   const size_t smem = 3 * (size_t)C * sizeof(float);
   bool done = false;
 #define X(L, N)                                                                                                      \
   if (!done && lpr == L && nv == N) {                                                                                \
     done = true;                                                                                                     \
-    if (dy_is_bf16)                                                                                                  \
-      add_ln_bwd_kernel<L, N, bf16><<<grid, threads, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep,  \
-                                                                 tokens_per_sample, dx, (bf16*)ddelta, dgamma, dbeta, \
-                                                                 ddelta_bias, T, C);                                 \
+    if (dy_is_bf16 && (N > 3 || occ == 3))                                                                           \
+      add_ln_bwd_kernel<L, N, bf16, 3><<<grid, threads, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep, \
+                                                                    tokens_per_sample, dx, (bf16*)ddelta, dgamma,     \
+                                                                    dbeta, ddelta_bias, T, C);                        \
+    else if (dy_is_bf16)                                                                                             \
+      add_ln_bwd_kernel<L, N, bf16, 2><<<grid, threads, smem, st>>>((const bf16*)dy, dxo, xs, mean, rstd, gamma, keep, \
+                                                                    tokens_per_sample, dx, (bf16*)ddelta, dgamma,     \
+                                                                    dbeta, ddelta_bias, T, C);                        \
     else                                                                                                             \
-      add_ln_bwd_kernel<L, N, float><<<grid, threads, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma,      \
-                                                                  keep, tokens_per_sample, dx, (bf16*)ddelta, dgamma, \
-                                                                  dbeta, ddelta_bias, T, C);                         \
+      add_ln_bwd_kernel<L, N, float, 3><<<grid, threads, smem, st>>>((const float*)dy, dxo, xs, mean, rstd, gamma,   \
+                                                                     keep, tokens_per_sample, dx, (bf16*)ddelta,      \
+                                                                     dgamma, dbeta, ddelta_bias, T, C);               \
   }
   ADDLN_COMBOS(X)
 #undef X

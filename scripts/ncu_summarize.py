@@ -77,8 +77,12 @@ def kernel_cases():
         commit = "?"
     out = ["# ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <n> -c 1 python scripts/ncu_kernels.py <case>",
            "# one launch of each hot kernel at a known shape of the Swin-T B=64 step; algorithmic bytes / flops from scripts/ncu_kernels.py"]
-    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = json.load(open(tpath)) if os.path.isfile(tpath) else {}   # captures of other cases are kept
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--cases=")]
     for case, meta in cases.items():
+        if only and case not in only[0]:
+            continue
         rep = os.path.join(ROOT, "gpurun_out", f"k_{case}.ncu-rep")
         csvp = os.path.join(ROOT, "gpurun_out", f"k_{case}.csv")
         if os.path.isfile(csvp) and os.path.getsize(csvp) > 100:
@@ -122,7 +126,7 @@ def kernel_cases():
     for k, c in alias.items():
         if c in traffic:
             traffic[k] = traffic[c]
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+    json.dump(traffic, open(tpath, "w"), indent=1)
     print("\n".join(out))
 
 
