@@ -217,6 +217,8 @@ __device__ __forceinline__ void pe_gather_tile(const float* __restrict__ img, fl
 template <int EJ>
 __device__ __forceinline__ void pe_conv_tile(const float* As, const float* Ws, const float* bj, int E, int tg, int cg,
                                              float (&acc)[4][EJ]) {
+  // (packed fma.rn.f32x2 over token pairs measured SLOWER here: the shared weight must be duplicated into a register pair
+  // per FMA pair; the weight-gradient loop of the backward, whose operands are natural pairs, does use it)
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -313,11 +315,14 @@ __global__ void __launch_bounds__(256) patch_embed_bwd2_kernel(
 #pragma unroll
   for (int j = 0; j < EJ; j++) { bj[j] = bias[cg + 16 * j]; gj[j] = gamma[cg + 16 * j]; }
   const float invE = 1.f / (float)E;
-  float adw[3][EJ], adb[EJ], adg[EJ], adbe[EJ];  // this thread's dW[e = cg+16j][k = tg*3 + kk] and per-channel sums
+  // this thread's dW[e = cg+16j][k = tg*3 + kk] (two partial sums each: even / odd token pairs, packed FMAs) and
+  // per-channel sums
+  float2 adw[3][EJ];
+  float adb[EJ], adg[EJ], adbe[EJ];
 #pragma unroll
   for (int j = 0; j < EJ; j++) {
     adb[j] = adg[j] = adbe[j] = 0.f;
-    adw[0][j] = adw[1][j] = adw[2][j] = 0.f;
+    adw[0][j] = adw[1][j] = adw[2][j] = make_float2(0.f, 0.f);
   }
   for (long long t0 = (long long)blockIdx.x * PE_TM; t0 < T; t0 += (long long)gridDim.x * PE_TM) {
     __syncthreads();
@@ -364,8 +369,10 @@ __global__ void __launch_bounds__(256) patch_embed_bwd2_kernel(
       for (int j = 0; j < EJ; j++) {
         const float4 d = *reinterpret_cast<const float4*>(Ds + (cg + 16 * j) * PE_LDA + t4 * 4);
 #pragma unroll
-        for (int kk = 0; kk < 3; kk++)
-          adw[kk][j] += (a[kk].x * d.x + a[kk].y * d.y) + (a[kk].z * d.z + a[kk].w * d.w);
+        for (int kk = 0; kk < 3; kk++) {
+          adw[kk][j] = __ffma2_rn(make_float2(a[kk].x, a[kk].y), make_float2(d.x, d.y), adw[kk][j]);
+          adw[kk][j] = __ffma2_rn(make_float2(a[kk].z, a[kk].w), make_float2(d.z, d.w), adw[kk][j]);
+        }
       }
     }
   }
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(256) patch_embed_bwd2_kernel(
   for (int j = 0; j < EJ; j++) {
     const int e = cg + 16 * j;
 #pragma unroll
-    for (int kk = 0; kk < 3; kk++) atomicAdd(&dw[e * PE_K + tg * 3 + kk], adw[kk][j]);
+    for (int kk = 0; kk < 3; kk++) atomicAdd(&dw[e * PE_K + tg * 3 + kk], adw[kk][j].x + adw[kk][j].y);
     atomicAdd(&red[e], adb[j]);
     atomicAdd(&red[E + e], adg[j]);
     atomicAdd(&red[2 * E + e], adbe[j]);
