@@ -521,10 +521,11 @@ def main():
                 torch.cuda.synchronize()
             rows = [e for e in prof2.key_averages(group_by_input_shape=True, group_by_stack_n=8)
                     if e.key in ("aten::copy_", "aten::add_", "aten::add", "aten::fill_", "aten::zero_", "aten::cat",
-                                 "aten::clone", "aten::contiguous", "aten::sum")]
+                                 "aten::clone", "aten::contiguous", "aten::sum", "aten::mul", "aten::mul_", "aten::div",
+                                 "aten::_to_copy", "aten::index", "aten::where", "aten::stack")]
             rows.sort(key=lambda e: -e.count)
             with open(args.profile + ".stacks.txt", "w") as f:
-                for e in rows[:60]:
+                for e in rows[:90]:
                     f.write(f"{e.key} x{e.count} cuda_total={e.device_time_total:.0f}us shapes={e.input_shapes}\n")
                     for fr in e.stack[:8]:
                         f.write(f"      {fr}\n")

@@ -191,7 +191,16 @@ class SelfDistillStep:
         caller's crops into them on the current stream, so the caller may recycle its own (prefetch) buffers freely.  A
         batch of a different shape (e.g. a shorter last batch) runs the eager body instead."""
         if self._static_in is None:
-            self._static_in = [torch.empty_like(im) for im in images]
+            # crops of one shape share one buffer, back to back: the multi-crop forward then views a resolution group
+            # as one batch instead of concatenating it (ops.cat_adjacent)
+            self._static_in, i = [], 0
+            while i < len(images):
+                j = i
+                while j < len(images) and images[j].shape == images[i].shape and images[j].dtype == images[i].dtype:
+                    j += 1
+                buf = torch.empty((j - i,) + tuple(images[i].shape), dtype=images[i].dtype, device=images[i].device)
+                self._static_in += [buf[k] for k in range(j - i)]
+                i = j
         if len(images) != len(self._static_in) or any(s.shape != im.shape for s, im in zip(self._static_in, images)):
             return self._body(images, epoch)
         for s, im in zip(self._static_in, images):

@@ -182,6 +182,37 @@ class LayerNormFn(Function):
         return (dx, acc[0], acc[1], None, None) if first else (dx, None, None, None, None)
 
 
+class LayerNormResidFn(Function):
+    """x fp32 -> (x, y = LN(x)): the start of a residual stream whose input is also the shortcut (the first block after
+    PatchEmbed).  Handing x out as an OUTPUT makes autograd deliver the shortcut's gradient to this backward, where the
+    add_ln backward kernel adds it to the LN input gradient (dxo) - otherwise x has two consumers and autograd sums the
+    two full-size fp32 gradients with a separate add kernel (112 us for Swin-T at B = 64)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, y_bf16: bool):
+        x = _chk(x, F32, "x")
+        gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        _, y, mean, rstd = _add_ln_fwd(x, None, None, 1, gamma, beta, eps, True, y_bf16)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.y_bf16 = y_bf16
+        return x.view(x.shape), y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_x, g_y):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        T, C = x.numel() // x.shape[-1], x.shape[-1]
+        g_x = _chk(g_x, F32, "g_x") if g_x is not None else None
+        if g_y is None:
+            return g_x, None, None, None, None
+        g_y = _chk(g_y, BF16 if ctx.y_bf16 else F32, "g_y")
+        dx = torch.empty_like(x)
+        acc, first = _acc(("ln", gamma.data_ptr()), (2, C), x.device)
+        _lib.call("esvit_add_ln_bwd", _p(g_y), 1 if ctx.y_bf16 else 0, _p(g_x), _p(x), _p(mean), _p(rstd), _p(gamma),
+                  None, 1, _p(dx), None, _p(acc[0]), _p(acc[1]), None, T, C, _stream())
+        return (dx, acc[0], acc[1], None, None) if first else (dx, None, None, None, None)
+
+
 class ResidualAddFn(Function):
     """xout = x + keep * delta (fp32 + bf16), no norm; delta_bias only receives its gradient (see AddLayerNormFn)."""
 
@@ -212,6 +243,8 @@ class ResidualAddFn(Function):
 def add_layer_norm(x: Tensor, delta: Optional[Tensor], keep: Optional[Tensor], gamma: Tensor, beta: Tensor,
                    eps: float, y_bf16: bool = True, delta_bias: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     if delta is None:
+        if x.requires_grad and torch.is_grad_enabled():
+            return LayerNormResidFn.apply(x, gamma, beta, eps, y_bf16)
         return x, LayerNormFn.apply(x, gamma, beta, eps, y_bf16)
     return AddLayerNormFn.apply(x, delta, delta_bias, keep, gamma, beta, eps, y_bf16)  # x may be None: xout = fp32(delta)
 
@@ -310,6 +343,73 @@ class PatchEmbedFn(Function):
         _lib.call("esvit_patch_embed_bwd", _p(img), _p(w), _p(bias), _p(gamma), _p(mean), _p(rstd), _p(g), _p(dw),
                   _p(db), _p(dgamma), _p(dbeta), B, H, W, E, _stream())
         return (None, dw, db, dgamma, dbeta, None) if first else (None, None, None, None, None, None)
+
+
+class PatchEmbedGroupsFn(Function):
+    """PatchEmbedFn over several resolution groups written into ONE token buffer fp32 [sum_g B_g L_g, E] (the
+    concatenated residual stream of the fused multi-crop forward): no torch.cat of the groups' outputs (267 MB copied
+    per step for Swin-T at B = 64) and no split of the gradient."""
+
+    @staticmethod
+    def forward(ctx, w, bias, gamma, beta, eps: float, *imgs):
+        w, bias = _chk(w, F32, "w"), _chk(bias, F32, "bias")
+        gamma, beta = _chk(gamma, F32, "gamma"), _chk(beta, F32, "beta")
+        imgs = [_chk(im, F32, "img") for im in imgs]
+        E = w.shape[0]
+        if tuple(w.shape[1:]) != (3, 4, 4) or any(im.shape[1] != 3 for im in imgs):
+            raise ValueError("PatchEmbed kernel supports in_chans=3, patch_size=4")
+        rows = [im.shape[0] * (im.shape[2] // 4) * (im.shape[3] // 4) for im in imgs]
+        T = sum(rows)
+        dev = imgs[0].device
+        out = torch.empty(T, E, dtype=F32, device=dev)
+        mean = torch.empty(T, dtype=F32, device=dev)
+        rstd = torch.empty(T, dtype=F32, device=dev)
+        r0 = 0
+        for im, n in zip(imgs, rows):
+            B, _, H, W = im.shape
+            _lib.call("esvit_patch_embed_fwd", _p(im), _p(w), _p(bias), _p(gamma), _p(beta), eps, _p(out[r0:]),
+                      _p(mean[r0:]), _p(rstd[r0:]), B, H, W, E, _stream())
+            r0 += n
+        ctx.save_for_backward(w, bias, gamma, mean, rstd, *imgs)
+        ctx.rows = rows
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        w, bias, gamma, mean, rstd = ctx.saved_tensors[:5]
+        imgs = ctx.saved_tensors[5:]
+        E = w.shape[0]
+        g = _chk(g, F32, "g")
+        dw, first = _acc(("pe_w", w.data_ptr()), tuple(w.shape), w.device)
+        acc, _ = _acc(("pe_b", w.data_ptr()), (3, E), w.device)
+        r0 = 0
+        for im, n in zip(imgs, ctx.rows):
+            B, _, H, W = im.shape
+            _lib.call("esvit_patch_embed_bwd", _p(im), _p(w), _p(bias), _p(gamma), _p(mean[r0:]), _p(rstd[r0:]),
+                      _p(g[r0:]), _p(dw), _p(acc[0]), _p(acc[1]), _p(acc[2]), B, H, W, E, _stream())
+            r0 += n
+        none = (None,) * len(imgs)
+        return ((dw, acc[0], acc[1], acc[2], None) if first else (None, None, None, None, None)) + none
+
+
+def cat_adjacent(ts):
+    """torch.cat(ts) along dim 0 - as a VIEW when the tensors already lie back to back in one storage (the engine's
+    static crop buffers do: the 2 global / 8 local crops of a step), so the multi-crop forward copies nothing."""
+    ts = list(ts)
+    if len(ts) == 1:
+        return ts[0]
+    t0 = ts[0]
+    ok = all(t.shape == t0.shape and t.dtype == t0.dtype and t.device == t0.device and t.is_contiguous()
+             and not t.requires_grad for t in ts)
+    if ok:
+        st, n = t0.untyped_storage(), t0.numel()
+        ok = all(t.untyped_storage().data_ptr() == st.data_ptr() and t.storage_offset() == t0.storage_offset() + i * n
+                 for i, t in enumerate(ts))
+    if not ok:
+        return torch.cat(ts)
+    shape = (t0.shape[0] * len(ts),) + tuple(t0.shape[1:])
+    return torch.as_strided(t0, shape, t0.stride(), t0.storage_offset())
 
 
 # ------------------------------------------------------------------------------------------------------------

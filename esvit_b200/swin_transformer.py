@@ -451,15 +451,16 @@ class SwinTransformer(nn.Module):
     def _forward_fused_groups(self, x, groups, cc):
         """Multi-crop forward with ONE pass over the concatenated tokens of all resolution groups for every per-token op
         (same math and output order as the per-group loop of models/swin_transformer.py:713-763)."""
-        feats, grp, row0 = [], [], 0
+        imgs, grp, row0 = [], [], 0
         for s, e in groups:
-            t = self.patch_embed(torch.cat(x[s:e]) if e - s > 1 else x[s])  # fp32 [B, L, E]
-            B, L, E = t.shape
-            H = W = int(math.sqrt(L))
-            feats.append(t.reshape(B * L, E))
+            im = ops.cat_adjacent(x[s:e]).float()
+            B, H, W = im.shape[0], im.shape[2] // 4, im.shape[3] // 4
+            imgs.append(im)
             grp.append((B, H, W, row0))
-            row0 += B * L
-        xa = torch.cat(feats) if len(feats) > 1 else feats[0]
+            row0 += B * H * W
+        pe = self.patch_embed
+        # every group's tokens straight into the concatenated stream (fp32 [T, E]); same kernels as PatchEmbed.forward
+        xa = ops.PatchEmbedGroupsFn.apply(pe.proj.weight, pe.proj.bias, pe.norm.weight, pe.norm.bias, pe.norm.eps, *imgs)
         dev = xa.device
         keeps_all = None
         if self.training and any(blk.drop_prob > 0. for layer in self.layers for blk in layer.blocks):
@@ -519,7 +520,7 @@ class SwinTransformer(nn.Module):
             cls_l, fea_l, npatch = [], [], []
             for gi, (s, e) in enumerate(groups):
                 cc.group = gi
-                pooled, region = self.forward_features(torch.cat(x[s:e]) if e - s > 1 else x[s], cc)
+                pooled, region = self.forward_features(ops.cat_adjacent(x[s:e]), cc)
                 B, N, C = region.shape
                 cls_l.append(pooled)
                 fea_l.append(region.reshape(B * N, C))

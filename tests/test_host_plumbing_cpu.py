@@ -111,3 +111,18 @@ def test_loss_row_order_is_an_image_major_permutation():
     assert all(imgs[i * per] == i for i in range(B))
     oc = m._order(B, [(ncrops, 1)], "cpu").tolist()  # cls rows: (crop, image) -> (image, crop)
     assert oc == [v * B + b for b in range(B) for v in range(ncrops)]
+
+
+def test_cat_adjacent_views_back_to_back_crops():
+    """ops.cat_adjacent == torch.cat; a view (no copy) exactly when the tensors lie back to back in one storage."""
+    import torch
+    from esvit_b200 import ops
+    buf = torch.randn(3, 4, 3, 8, 8)
+    ts = [buf[k] for k in range(3)]
+    v = ops.cat_adjacent(ts)
+    assert torch.equal(v, torch.cat(ts)) and v.data_ptr() == buf.data_ptr()
+    gap = ops.cat_adjacent([buf[0], buf[2]])                       # not adjacent: a real concatenation
+    assert torch.equal(gap, torch.cat([buf[0], buf[2]])) and gap.data_ptr() != buf.data_ptr()
+    sep = [torch.randn(4, 3, 8, 8) for _ in range(2)]               # separate allocations
+    assert torch.equal(ops.cat_adjacent(sep), torch.cat(sep))
+    assert ops.cat_adjacent([buf[1]]) is not None and ops.cat_adjacent([buf[1]]).shape == buf[1].shape
