@@ -329,7 +329,7 @@ def main():
     l = one_step(crops)  # first step untimed: lazy module loading / attribute calls must not pollute the per-kernel timings
     torch.cuda.synchronize()
     _lib.reset_counters()
-    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_dino_ce_fwd", "esvit_window_attn_bwd", "esvit_window_attn_fwd",
+    _lib.time_entry_point(["esvit_dino_ce_bwd", "esvit_dino_ce_fwd", "esvit_dino_ce_q_bwd", "esvit_dino_ce_q_fwd", "esvit_row_softmax_q", "esvit_window_attn_bwd", "esvit_window_attn_fwd",
                             "esvit_gemm_bias_act", "esvit_gemm_mul_colsum", "esvit_gemm_bf16", "esvit_gemm_mul_colsum2",
                             "esvit_gemm_wgrad", "esvit_add_ln_fwd", "esvit_add_ln_bwd", "esvit_patch_embed_fwd",
                             "esvit_patch_embed_bwd"])
@@ -431,6 +431,10 @@ def main():
         Tg, Tl = 49, 9
         rows_s = B * (2 * Tg + n_local * Tl)
         rows_t = B * 2 * Tg
+        # the CE kernels run on stored teacher probabilities (esvit_dino_ce_q_*) unless ESVIT_CE_Q=0
+        used_q = any(t["name"] == "esvit_dino_ce_q_fwd" for t in timed)
+        ce_q = "_q" if used_q else ""
+        ce_fwd_name, ce_bwd_name = "esvit_dino_ce%s_fwd" % ce_q, "esvit_dino_ce%s_bwd" % ce_q
         # attention backward (the largest of this repo's kernels by time): reads qkv (6C) + dO (2C) + O (2C), writes dqkv
         # (6C) bytes per token -> 16*C per token; forward: 8*C per token
         wtag = "7_kernel" if "w14" not in args.arch else "14_kernel + 7_kernel (stage 3)"
@@ -438,7 +442,7 @@ def main():
         r_fwd = agg("esvit_window_attn_fwd", lambda t: 8 * t["tokens"] * t["C"], f"window_attn_fwd{wtag} (all launches of a step)")
         # region-row CE backward: read student rows + each paired teacher row once + write bf16 grads:
         # (170 + 98 + 170) rows x K x 2 B per image
-        r_ce = agg("esvit_dino_ce_bwd", lambda t: (2 * rows_s + rows_t) * t["K"] * 2, "dino_ce_bwd_kernel (region rows)",
+        r_ce = agg(ce_bwd_name, lambda t: (2 * rows_s + rows_t) * t["K"] * 2, "dino_ce%s_bwd_kernel (region rows)" % ce_q,
                    extra=lambda t: t["rows"] == rows_s)
         # tcgen05 fc1 GEMM + bias + GELU: reads A (M*K) and W, writes out and gelu' (2*M*N) in bf16
         r_gemm = agg("esvit_gemm_bias_act", lambda t: 2 * (t["M"] * t["K"] + t["N"] * t["K"] + 2 * t["M"] * t["N"]),
@@ -482,16 +486,18 @@ def main():
         r_lnf = agg("esvit_add_ln_fwd", lambda t: t["T"] * t["C"] * ((4 if t["has_x"] else 0) + (2 if t["has_delta"] else 0) + 4 + 2),
                     "add_ln_fwd_kernel (all launches of a step)")
         r_lnb = agg("esvit_add_ln_bwd", lambda t: 16 * t["T"] * t["C"], "add_ln_bwd_kernel (all launches of a step)")
-        r_cef = agg("esvit_dino_ce_fwd", lambda t: (rows_s + rows_t) * t["K"] * 2, "dino_ce_fwd_kernel (region rows)",
+        r_cef = agg(ce_fwd_name, lambda t: (rows_s + rows_t) * t["K"] * 2, "dino_ce%s_fwd_kernel (region rows)" % ce_q,
                     extra=lambda t: t["rows"] == rows_s)
         r_pef = agg("esvit_patch_embed_fwd", lambda t: t["B"] * (3 * t["H"] * t["W"] * 4 + (t["H"] // 4) * (t["W"] // 4) * t["E"] * 4),
                     "patch_embed_fwd2_kernel (all launches of a step)")
         r_peb = agg("esvit_patch_embed_bwd", lambda t: t["B"] * (3 * t["H"] * t["W"] * 4 + (t["H"] // 4) * (t["W"] // 4) * t["E"] * 4),
                     "patch_embed_bwd2_kernel (all launches of a step)")
+        # teacher rows once: read bf16 logits, write fp16 probabilities (all launches: cls + region rows)
+        r_rsq = agg("esvit_row_softmax_q", lambda t: t["rows"] * t["K"] * 4, "row_softmax_q_kernel (all teacher rows of a step)")
         for r, key in ((g_fwd, "gemm_bf16"), (g_mul, "gemm_mul_colsum"), (g_wgr, "gemm_wgrad"), (r_lnf, "add_ln_fwd"), (r_lnb, "add_ln_bwd")):
             if r and key in traffic:
                 r["traffic"] = traffic[key]
-        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm, r_gemm2, g_fwd, g_dgr, g_mul, g_wgr, r_lnf, r_lnb, r_cef, r_pef, r_peb) if r]
+        cands = [r for r in (r_bwd, r_fwd, r_ce, r_gemm, r_gemm2, g_fwd, g_dgr, g_mul, g_wgr, r_lnf, r_lnb, r_cef, r_pef, r_peb, r_rsq) if r]
         if cands:
             cands.sort(key=lambda r: -r["ms_per_step"])
             roofline, roofline_others = cands[0], cands[1:]

@@ -48,6 +48,10 @@ SIGNATURES = {
     "esvit_dino_ce_fwd": [P, P, P, P, P, P, P, F, F, P, L, I, P],
     "esvit_dino_ce_bwd": [P, P, P, P, P, P, P, P, P, F, F, P, L, I, P],
     "esvit_weighted_sum": [P, P, I, P, P],
+    "esvit_row_softmax_q_max_k": [],
+    "esvit_row_softmax_q": [P, P, F, P, P, L, I, P],
+    "esvit_dino_ce_q_fwd": [P, P, P, P, P, F, P, L, I, P],
+    "esvit_dino_ce_q_bwd": [P, P, P, P, P, P, P, F, P, L, I, P],
     "esvit_colsum_workspace_rows": [],
     "esvit_colsum": [P, L, I, P, P, P],
     "esvit_center_ema": [P, P, F, F, P, I, P],
@@ -124,6 +128,9 @@ _META = {
                                    "has_delta": a[1] is not None and a[1].value is not None},
     "esvit_add_ln_bwd": lambda a: {"T": int(a[-3]), "C": int(a[-2])},
     "esvit_dino_ce_fwd": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
+    "esvit_dino_ce_q_fwd": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
+    "esvit_dino_ce_q_bwd": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
+    "esvit_row_softmax_q": lambda a: {"rows": int(a[-3]), "K": int(a[-2])},
     "esvit_patch_embed_fwd": lambda a: {"B": int(a[-5]), "H": int(a[-4]), "W": int(a[-3]), "E": int(a[-2])},
     "esvit_patch_embed_bwd": lambda a: {"B": int(a[-5]), "H": int(a[-4]), "W": int(a[-3]), "E": int(a[-2])},
 }

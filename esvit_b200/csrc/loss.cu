@@ -10,6 +10,7 @@
 //   d loss / d s_{r,k} = w_r / tau_s * ( n_r softmax(s~_r)_k - sum_j q_{t_j(r),k} )
 // The teacher rows of a region row are the cosine arg-max matches (region_match below); for a cls row
 // they are the same image's other global view(s).  Nothing of size [B, T, K] is ever materialised.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -313,6 +314,183 @@ __global__ void __launch_bounds__(256) region_match_kernel(const float* __restri
   }
 }
 
+
+// ---- teacher probabilities stored once (fp16, scaled by 2^12) -----------------------------------------------------------
+// Every teacher row is paired with ~3.5 student rows (cls: 4 - 8 crops of the image, regions: the arg-max matches), and
+// both CE kernels were bound by the SFU / FMA pipes, not by HBM: 3 exponentials per student logit, two of them teacher
+// terms recomputed for every pairing.  row_softmax_q_kernel computes q = softmax((t - center) / temp) once per teacher row
+// (LSE pass, then exp pass over the same row while it is still in L2: one DRAM read) and stores q * 2^12 in fp16: 11
+// significant bits down to q = 1.5e-8 (below that, flushed: < 1e-3 of the probability mass even for a uniform row of
+// 65536).  The CE kernels then stream q like the student logits.
+__device__ __forceinline__ float fast_ex2(float x) {   // ex2.approx (one SFU instruction), as __expf uses
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr int QT = 512;             // threads of the row-softmax CTA (4 CTAs per SM)
+constexpr float Q_SCALE_LOG2 = 12.f, Q_UNSCALE = 1.f / 4096.f;
+struct __align__(16) half8 { __half2 v[4]; };
+__device__ __forceinline__ void unpack_h8(const half8& h, float* f) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) { const float2 t = __half22float2(h.v[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+
+// Two passes over the row: LSE, then q.  The second pass re-reads the 2 K bytes this CTA has just streamed: an L2 hit (the
+// rows in flight on the whole GPU, 592 x 128 KB, fit the 126 MB L2).  A first version kept the row in shared memory: one
+// CTA per SM, its load, reduce and store phases never overlapped, 3x the HBM time.
+__global__ void __launch_bounds__(QT, 4) row_softmax_q_kernel(const bf16* __restrict__ x, const float* __restrict__ center,
+                                                              float inv_temp, float* __restrict__ lse, half8* __restrict__ q, int K) {
+  __shared__ float red_m[QT / 32], red_s[QT / 32];
+  __shared__ float lse2_sh;
+  const long long r = blockIdx.x;
+  const bf16x8* xr = reinterpret_cast<const bf16x8*>(x + r * K);
+  const float a = inv_temp * 1.4426950408889634f;          // exp(v * inv_temp) = exp2(v * a)
+  float m = -INFINITY, s = 0.f;                            // online (max, sum) in the exp2 domain
+#pragma unroll 4
+  for (int i = threadIdx.x; i < K / 8; i += QT) {   // (unrolled: four independent row loads in flight per thread)
+    float f[8];
+    unpack8(xr[i], f);
+    const float4 c0 = *reinterpret_cast<const float4*>(center + i * 8), c1 = *reinterpret_cast<const float4*>(center + i * 8 + 4);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    float lm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { f[j] = (f[j] - c[j]) * a; lm = fmaxf(lm, f[j]); }
+    if (lm > m) { s *= fast_ex2(m - lm); m = lm; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += fast_ex2(f[j] - m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = (m == -INFINITY ? 0.f : s * fast_ex2(m - nm)) + (om == -INFINITY ? 0.f : os * fast_ex2(om - nm));
+    m = nm;
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red_m[w] = m; red_s[w] = s; }
+  __syncthreads();
+  if (w == 0) {
+    m = l < QT / 32 ? red_m[l] : -INFINITY;
+    s = l < QT / 32 ? red_s[l] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+      const float nm = fmaxf(m, om);
+      s = (m == -INFINITY ? 0.f : s * fast_ex2(m - nm)) + (om == -INFINITY ? 0.f : os * fast_ex2(om - nm));
+      m = nm;
+    }
+    if (l == 0) {
+      const float lse2 = m + log2f(s);
+      lse2_sh = lse2;
+      lse[r] = lse2 * 0.6931471805599453f;                 // natural-log LSE (what esvit_row_lse returns)
+    }
+  }
+  __syncthreads();
+  const float off = Q_SCALE_LOG2 - lse2_sh;
+  half8* qr = q + r * (K / 8);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < K / 8; i += QT) {   // (unrolled: four independent row loads in flight per thread)
+    float f[8];
+    unpack8(xr[i], f);
+    const float4 c0 = *reinterpret_cast<const float4*>(center + i * 8), c1 = *reinterpret_cast<const float4*>(center + i * 8 + 4);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    half8 h;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      h.v[k] = __floats2half2_rn(fast_ex2(fmaf(f[2 * k] - c[2 * k], a, off)), fast_ex2(fmaf(f[2 * k + 1] - c[2 * k + 1], a, off)));
+    qr[i] = h;
+  }
+}
+
+// the CE kernels on stored teacher probabilities (q12 = q * 2^12, fp16 [Rt, K]): same contract as dino_ce_fwd / bwd
+__global__ void __launch_bounds__(LT) dino_ce_q_fwd_kernel(
+    const bf16* __restrict__ s, const half8* __restrict__ q12, float* __restrict__ lse_s, const int* __restrict__ trow,
+    float inv_tau_s, float* __restrict__ row_loss, int K, const int* __restrict__ order) {
+  const long long r = order ? order[blockIdx.x] : blockIdx.x;
+  const int t0 = trow[2 * r], t1 = trow[2 * r + 1];
+  const bf16x8* sr = reinterpret_cast<const bf16x8*>(s + r * K);
+  const half8* q0 = t0 >= 0 ? q12 + (long long)t0 * (K / 8) : nullptr;
+  const half8* q1 = t1 >= 0 ? q12 + (long long)t1 * (K / 8) : nullptr;
+  const float a = inv_tau_s * 1.4426950408889634f;
+  float acc = 0.f, m = -INFINITY, sm = 0.f;                // (m, sm): student online softmax in the exp2 domain
+  for (int i = threadIdx.x; i < K / 8; i += LT) {
+    float fs[8], qq[8];
+    unpack8(sr[i], fs);
+#pragma unroll
+    for (int j = 0; j < 8; j++) qq[j] = 0.f;
+    if (q0) {
+      float ft[8];
+      unpack_h8(q0[i], ft);
+#pragma unroll
+      for (int j = 0; j < 8; j++) qq[j] += ft[j];
+    }
+    if (q1) {
+      float ft[8];
+      unpack_h8(q1[i], ft);
+#pragma unroll
+      for (int j = 0; j < 8; j++) qq[j] += ft[j];
+    }
+    float lm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      acc = fmaf(qq[j], fs[j], acc);
+      fs[j] *= a;
+      lm = fmaxf(lm, fs[j]);
+    }
+    if (lm > m) { sm *= fast_ex2(m - lm); m = lm; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) sm += fast_ex2(fs[j] - m);
+  }
+  // (max, sum) pairs are combined in the natural-log domain by block_reduce_ms
+  m *= 0.6931471805599453f;
+  block_reduce_ms(m, sm);
+  __shared__ float lse_sh;
+  if (threadIdx.x == 0) lse_sh = m + logf(sm);
+  acc = block_sum(acc);  // (contains the __syncthreads that publishes lse_sh)
+  if (threadIdx.x == 0) {
+    const float n = (float)((t0 >= 0) + (t1 >= 0));
+    lse_s[r] = lse_sh;
+    row_loss[r] = n * lse_sh - acc * (inv_tau_s * Q_UNSCALE);
+  }
+}
+
+__global__ void __launch_bounds__(LT) dino_ce_q_bwd_kernel(
+    const bf16* __restrict__ s, const half8* __restrict__ q12, const float* __restrict__ lse_s, const int* __restrict__ trow,
+    const float* __restrict__ w, const float* __restrict__ gscale, float inv_tau_s, bf16* __restrict__ ds, int K,
+    const int* __restrict__ order) {
+  const long long r = order ? order[blockIdx.x] : blockIdx.x;
+  const int t0 = trow[2 * r], t1 = trow[2 * r + 1];
+  const bf16x8* sr = reinterpret_cast<const bf16x8*>(s + r * K);
+  bf16x8* dr = reinterpret_cast<bf16x8*>(ds + r * K);
+  const half8* q0 = t0 >= 0 ? q12 + (long long)t0 * (K / 8) : nullptr;
+  const half8* q1 = t1 >= 0 ? q12 + (long long)t1 * (K / 8) : nullptr;
+  const float n = (float)((t0 >= 0) + (t1 >= 0));
+  const float coef = gscale[0] * w[r] * inv_tau_s;
+  const float a = inv_tau_s * 1.4426950408889634f, ls2 = lse_s[r] * 1.4426950408889634f;
+  const float cn = coef * n, cq = -coef * Q_UNSCALE;
+  for (int i = threadIdx.x; i < K / 8; i += LT) {
+    float fs[8], qq[8], g[8];
+    unpack8(sr[i], fs);
+#pragma unroll
+    for (int j = 0; j < 8; j++) qq[j] = 0.f;
+    if (q0) {
+      float ft[8];
+      unpack_h8(q0[i], ft);
+#pragma unroll
+      for (int j = 0; j < 8; j++) qq[j] += ft[j];
+    }
+    if (q1) {
+      float ft[8];
+      unpack_h8(q1[i], ft);
+#pragma unroll
+      for (int j = 0; j < 8; j++) qq[j] += ft[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) g[j] = fmaf(cn, fast_ex2(fmaf(fs[j], a, -ls2)), cq * qq[j]);
+    dr[i] = pack8(g);
+  }
+}
+
 }  // namespace
 
 ESVIT_API int esvit_row_lse(const void* x, const float* center, float inv_temp, float* lse, long long R, int K,
@@ -337,6 +515,33 @@ ESVIT_API int esvit_dino_ce_bwd(const void* s, const void* t, const float* cente
   if (K % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
   dino_ce_bwd_kernel<<<(unsigned)R, LT, 0, (cudaStream_t)stream>>>((const bf16*)s, (const bf16*)t, center, lse_s, lse_t,
                                                                    trow, w, gscale, inv_temp_t, inv_tau_s, (bf16*)ds, K, order);
+  ESVIT_LAUNCH_CHECK();
+}
+
+// ---- the same loss on stored teacher probabilities (see row_softmax_q_kernel) ----
+ESVIT_API int esvit_row_softmax_q_max_k(void) { return 1 << 24; }  // (no structural limit: the row is streamed twice)
+
+ESVIT_API int esvit_row_softmax_q(const void* x, const float* center, float inv_temp, float* lse, void* q, long long R,
+                                  int K, void* stream) {
+  if (K % 8 != 0 || R <= 0 || !center || K > esvit_row_softmax_q_max_k()) return ESVIT_ERR_BAD_ARG;
+  row_softmax_q_kernel<<<(unsigned)R, QT, 0, (cudaStream_t)stream>>>((const bf16*)x, center, inv_temp, lse, (half8*)q, K);
+  ESVIT_LAUNCH_CHECK();
+}
+
+ESVIT_API int esvit_dino_ce_q_fwd(const void* s, const void* q, float* lse_s, const int* trow, const int* order,
+                                  float inv_tau_s, float* row_loss, long long R, int K, void* stream) {
+  if (K % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
+  dino_ce_q_fwd_kernel<<<(unsigned)R, LT, 0, (cudaStream_t)stream>>>((const bf16*)s, (const half8*)q, lse_s, trow, inv_tau_s,
+                                                                     row_loss, K, order);
+  ESVIT_LAUNCH_CHECK();
+}
+
+ESVIT_API int esvit_dino_ce_q_bwd(const void* s, const void* q, const float* lse_s, const int* trow, const int* order,
+                                  const float* w, const float* gscale, float inv_tau_s, void* ds, long long R, int K,
+                                  void* stream) {
+  if (K % 8 != 0 || R <= 0) return ESVIT_ERR_BAD_ARG;
+  dino_ce_q_bwd_kernel<<<(unsigned)R, LT, 0, (cudaStream_t)stream>>>((const bf16*)s, (const half8*)q, lse_s, trow, w, gscale,
+                                                                     inv_tau_s, (bf16*)ds, K, order);
   ESVIT_LAUNCH_CHECK();
 }
 

@@ -101,7 +101,7 @@ class DINOLoss(_CenteredLoss):
         n_terms = 2 * self.ncrops - 2
         trow, w = self._cls_tables(B, 1.0 / (n_terms * B), s.device)
         center = self._snapshot(self.center)
-        lse_t = ops.row_lse(t, center, 1.0 / temp)
+        lse_t = None if ops.ce_q_enabled(t.shape[-1]) else ops.row_lse(t, center, 1.0 / temp)
         loss = ops.DinoCEFn.apply(s, t, center, lse_t, trow, w, 1.0 / temp, 1.0 / self.student_temp,
                                   self._order(B, [(self.ncrops, 1)], s.device))
         self.update_center(t)
@@ -144,7 +144,8 @@ class DDINOLoss(_CenteredLoss):
 
         # view-level term (0.5 * DINO)
         trow_c, w_c = self._cls_tables(B, 0.5 / (n_terms * B), s_cls.device)
-        lse_tc = ops.row_lse(t_cls, center, inv_t)
+        use_q = ops.ce_q_enabled(t_cls.shape[-1])  # teacher probabilities stored once per row (ops.DinoCEFn)
+        lse_tc = None if use_q else ops.row_lse(t_cls, center, inv_t)
         loss_c = ops.DinoCEFn.apply(s_cls, t_cls, center, lse_tc, trow_c, w_c, inv_t, inv_s,
                                     self._order(B, [(self.ncrops, 1)], s_cls.device))
 
@@ -153,7 +154,7 @@ class DDINOLoss(_CenteredLoss):
             idx, trow_r = ops.region_match(s_fea.detach().float(), t_fea.detach().float(), B, self.ncrops, Tg, Tl)
             self.last_indices = idx
         w_r = self._region_weights(B, Tg, Tl, n_terms, s_reg.device)
-        lse_tr = ops.row_lse(t_reg, center_grid, inv_t)
+        lse_tr = None if use_q else ops.row_lse(t_reg, center_grid, inv_t)
         groups = [(2, Tg)] + ([(self.ncrops - 2, Tl)] if self.ncrops > 2 and Tl > 0 else [])
         loss_r = ops.DinoCEFn.apply(s_reg, t_reg, center_grid, lse_tr, trow_r, w_r, inv_t, inv_s,
                                     self._order(B, groups, s_reg.device))

@@ -855,38 +855,73 @@ def row_lse(x: Tensor, center: Optional[Tensor], inv_temp: float) -> Tensor:
     return lse
 
 
+def ce_q_enabled(K: int) -> bool:
+    """The CE kernels run on teacher probabilities stored once per teacher row (fp16, esvit_row_softmax_q) unless
+    ESVIT_CE_Q=0 or a row of K logits does not fit one CTA's shared memory."""
+    import os
+    return os.environ.get("ESVIT_CE_Q", "1") != "0" and K <= _lib.load().esvit_row_softmax_q_max_k()
+
+
+def row_softmax_q(x: Tensor, center: Tensor, inv_temp: float) -> Tuple[Tensor, Tensor]:
+    """(lse fp32 [R] as row_lse, q fp16 [R, K] = 2^12 * softmax((x - center) * inv_temp)): ONE pass over the teacher rows."""
+    x, center = _chk(x, BF16, "teacher logits"), _chk(center, F32, "center")
+    R, K = x.shape
+    lse = torch.empty(R, dtype=F32, device=x.device)
+    q = torch.empty(R, K, dtype=torch.float16, device=x.device)
+    _lib.call("esvit_row_softmax_q", _p(x), _p(center), inv_temp, _p(lse), _p(q), R, K, _stream())
+    return lse, q
+
+
 class DinoCEFn(Function):
     """loss = sum_r w[r] * ( n_r * LSE(s_r / tau) - sum_j <softmax((t[trow[r,j]] - center) / temp), s_r / tau> ).
 
-    s bf16 [R,K] (grad), t bf16 [Rt,K], center fp32 [K], trow int32 [R,2], w fp32 [R]."""
+    s bf16 [R,K] (grad), t bf16 [Rt,K], center fp32 [K], trow int32 [R,2], w fp32 [R].
+    lse_t = None (the default path): the teacher probabilities are computed ONCE per teacher row and stored in fp16
+    (row_softmax_q), the CE kernels stream them; lse_t = row_lse(t, center, inv_temp_t): every pairing recomputes the
+    teacher exponentials from the logits (the round-1 kernels)."""
 
     @staticmethod
     def forward(ctx, s, t, center, lse_t, trow, w, inv_temp_t: float, inv_tau_s: float, order=None):
         s, t = _chk(s, BF16, "student logits"), _chk(t, BF16, "teacher logits")
-        center, lse_t, w = _chk(center, F32, "center"), _chk(lse_t, F32, "lse_t"), _chk(w, F32, "w")
+        center, w = _chk(center, F32, "center"), _chk(w, F32, "w")
         trow = _chk(trow, torch.int32, "trow")
         order = _chk(order, torch.int32, "order")
         R, K = s.shape
         lse_s = torch.empty(R, dtype=F32, device=s.device)  # written by the CE kernel itself (one pass over s)
         row_loss = torch.empty(R, dtype=F32, device=s.device)
-        _lib.call("esvit_dino_ce_fwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(order), inv_temp_t, inv_tau_s,
-                  _p(row_loss), R, K, _stream())
+        ctx.use_q = lse_t is None
+        if ctx.use_q:
+            _, q = row_softmax_q(t, center, inv_temp_t)
+            _lib.call("esvit_dino_ce_q_fwd", _p(s), _p(q), _p(lse_s), _p(trow), _p(order), inv_tau_s, _p(row_loss), R, K,
+                      _stream())
+            ctx.save_for_backward(s, q, lse_s, trow, w, order)
+        else:
+            lse_t = _chk(lse_t, F32, "lse_t")
+            _lib.call("esvit_dino_ce_fwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(order), inv_temp_t,
+                      inv_tau_s, _p(row_loss), R, K, _stream())
+            ctx.save_for_backward(s, t, center, lse_s, lse_t, trow, w, order)
         loss = torch.empty((), dtype=F32, device=s.device)
         _lib.call("esvit_weighted_sum", _p(row_loss), _p(w), R, _p(loss), _stream())
-        ctx.save_for_backward(s, t, center, lse_s, lse_t, trow, w, order)
         ctx.temps = (inv_temp_t, inv_tau_s)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        s, t, center, lse_s, lse_t, trow, w, order = ctx.saved_tensors
         inv_temp_t, inv_tau_s = ctx.temps
-        R, K = s.shape
         gs = _chk(g.reshape(1).to(F32), F32, "g")
-        ds = torch.empty_like(s)
-        _lib.call("esvit_dino_ce_bwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(order), _p(w), _p(gs),
-                  inv_temp_t, inv_tau_s, _p(ds), R, K, _stream())
+        if ctx.use_q:
+            s, q, lse_s, trow, w, order = ctx.saved_tensors
+            R, K = s.shape
+            ds = torch.empty_like(s)
+            _lib.call("esvit_dino_ce_q_bwd", _p(s), _p(q), _p(lse_s), _p(trow), _p(order), _p(w), _p(gs), inv_tau_s, _p(ds),
+                      R, K, _stream())
+        else:
+            s, t, center, lse_s, lse_t, trow, w, order = ctx.saved_tensors
+            R, K = s.shape
+            ds = torch.empty_like(s)
+            _lib.call("esvit_dino_ce_bwd", _p(s), _p(t), _p(center), _p(lse_s), _p(lse_t), _p(trow), _p(order), _p(w),
+                      _p(gs), inv_temp_t, inv_tau_s, _p(ds), R, K, _stream())
         return ds, None, None, None, None, None, None, None, None
 
 

@@ -143,6 +143,18 @@ int esvit_dino_ce_bwd(const void* s, const void* t, const float* center, const f
                       const int* trow, const int* order, const float* w, const float* gscale, float inv_temp_t,
                       float inv_tau_s, void* ds, long long R, int K, void* stream);
 int esvit_weighted_sum(const float* v, const float* w, int R, float* out, void* stream);
+/* The same loss with the teacher probabilities stored once per teacher row (every teacher row is paired with ~3.5 student
+ * rows; recomputing its exponentials per pairing made both CE kernels SFU-bound):
+ * row_softmax_q: lse[r] as esvit_row_lse, q[r,k] = 2^12 * softmax((x[r] - center) * inv_temp)_k in fp16 [R,K]
+ *   (K <= esvit_row_softmax_q_max_k()).
+ * dino_ce_q_fwd / bwd: esvit_dino_ce_fwd / bwd with q (that fp16 tensor) in place of (t, center, lse_t, inv_temp_t). */
+int esvit_row_softmax_q_max_k(void);
+int esvit_row_softmax_q(const void* x, const float* center, float inv_temp, float* lse, void* q, long long R, int K,
+                        void* stream);
+int esvit_dino_ce_q_fwd(const void* s, const void* q, float* lse_s, const int* trow, const int* order, float inv_tau_s,
+                        float* row_loss, long long R, int K, void* stream);
+int esvit_dino_ce_q_bwd(const void* s, const void* q, const float* lse_s, const int* trow, const int* order,
+                        const float* w, const float* gscale, float inv_tau_s, void* ds, long long R, int K, void* stream);
 
 /* ---- update_center ----------------------------------------------------------- main_esvit.py:650-660, :752-770
  * colsum: out[k] = sum_r t[r,k] (deterministic two-stage); workspace fp32 [esvit_colsum_workspace_rows()*K].

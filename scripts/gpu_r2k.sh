@@ -1,9 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2t_pytest.log 2>&1; tail -3 gpurun_out/r2t_pytest.log
-ESVIT_PROFILE_STACKS=1 timeout 600 python bench.py --steps 20 --warmup 3 --no-gpu-reference --no-cpu-baseline --profile gpurun_out/r2t_prof.txt > gpurun_out/r2t_bench.json 2> gpurun_out/r2t_bench.err
-echo rc=$?; python -c "
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_real_shapes_gpu.py -x -q -m gpu -k "dino or loss or k65536" > gpurun_out/r2v_pytest.log 2>&1; tail -2 gpurun_out/r2v_pytest.log
+for q in 1 0 1; do
+ESVIT_CE_Q=$q timeout 600 python bench.py --steps 20 --warmup 3 --no-gpu-reference --no-cpu-baseline --no-e2e > gpurun_out/r2v_bench_q$q.json 2> gpurun_out/r2v_bench_q$q.err
+echo "CE_Q=$q rc=$?"; python -c "
 import json
-d=json.loads(open('gpurun_out/r2t_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('clocks'))"
-grep -v "^      " gpurun_out/r2t_prof.txt.stacks.txt | head -30
+d=json.loads(open('gpurun_out/r2v_bench_q$q.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'])
+for r in [d['roofline']]+d['roofline_others']:
+    if 'dino' in r['kernel'] or 'softmax' in r['kernel']: print('   ', r['kernel'][:60].ljust(60), round(r['frac'],3), round(r['ms_per_step'],3))"
+done

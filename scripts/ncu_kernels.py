@@ -27,8 +27,8 @@ CASES = {
     "attn_bwd7_s0": ("window_attn_bwd7", 16 * B_G * H_G * H_G * C0, 5 * 2 * 49 * 49 * 32 * 3 * B_G * 64, "ws 7 attention bwd, stage 0 global crops, shifted"),
     "add_ln_fwd_96": ("add_ln_fwd", 12 * T0 * C0, 0, "residual add + LN fwd, C = 96"),
     "add_ln_bwd_96": ("add_ln_bwd", 16 * T0 * C0, 0, "residual add + LN bwd, C = 96"),
-    "dino_ce_fwd": ("dino_ce_fwd", 2 * K_OUT * (ROWS_S + ROWS_T), 0, "CE fwd, region rows"),
-    "dino_ce_bwd": ("dino_ce_bwd", 2 * K_OUT * (2 * ROWS_S + ROWS_T), 0, "CE bwd, region rows"),
+    "dino_ce_fwd": ("dino_ce_q_fwd", 2 * K_OUT * (ROWS_S + ROWS_T), 0, "CE fwd, region rows"),
+    "dino_ce_bwd": ("dino_ce_q_bwd", 2 * K_OUT * (2 * ROWS_S + ROWS_T), 0, "CE bwd, region rows"),
     "patch_embed_fwd": ("patch_embed_fwd", 128 * 3 * 224 * 224 * 4 + 128 * 3136 * 96 * 4, 2 * 48 * 96 * 128 * 3136, "PatchEmbed fwd, global crops"),
     "patch_embed_bwd": ("patch_embed_bwd", 128 * 3 * 224 * 224 * 4 + 128 * 3136 * 96 * 4, 4 * 48 * 96 * 128 * 3136, "PatchEmbed bwd, global crops"),
     "region_match": ("region_match", 4 * 768 * (ROWS_S + ROWS_T), 2 * 768 * 49 * 64 * 2 * (49 + 8 * 9 + 49), "cosine arg-max"),

@@ -359,8 +359,10 @@ def _loss_inputs(B, ncrops, K, Tg, Tl, P, seed):
     return s_cls, t_cls, s_reg, t_reg, s_fea, t_fea, center, center_grid
 
 
+@pytest.mark.parametrize("ce_q", ["1", "0"])  # teacher probabilities stored once per row (default) / recomputed per pairing
 @pytest.mark.parametrize("K", [384, 4096])
-def test_dino_loss(K):
+def test_dino_loss(K, ce_q, monkeypatch):
+    monkeypatch.setenv("ESVIT_CE_Q", ce_q)
     from esvit_b200.losses import DINOLoss
     from oracle import losses as L
     B, ncrops = 3, 5
@@ -380,8 +382,10 @@ def test_dino_loss(K):
     assert_close(mod.center, c_r, 1e-5, "center")
 
 
+@pytest.mark.parametrize("ce_q", ["1", "0"])
 @pytest.mark.parametrize("K", [384, 4096])
-def test_ddino_loss(K):
+def test_ddino_loss(K, ce_q, monkeypatch):
+    monkeypatch.setenv("ESVIT_CE_Q", ce_q)
     from esvit_b200.losses import DDINOLoss
     from oracle import losses as L
     B, ncrops, Tg, Tl, P = 2, 5, 49, 9, 128
