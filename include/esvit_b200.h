@@ -67,7 +67,10 @@ int esvit_patch_embed_bwd(const float* img, const float* w, const float* bias, c
  * lane-expanded bias-gradient accumulator [nH][27][6][32], cleared and folded into dbias_table inside the call).
  * bias_ready (ws 7): 1 = bias_ws already holds the expansion written by esvit_window_attn_expand_bias for this table
  * (one expansion per table per step instead of one per call), 0 = the call expands it itself.
- * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] (complete qkv-bias gradient) ACCUMULATED. */
+ * bwd: dqkv fully written; dbias_table fp32 and dqkv_bias fp32 [3C] (complete qkv-bias gradient) ACCUMULATED.
+ * ws 7 backward: tcgen05 / TMEM kernel (five tensor-core GEMMs per window pair, dq/dk/dv through 4-D bulk tensor stores:
+ * qkv / dqkv / out rows must be 16-byte aligned, which C % 8 == 0 and a 16-byte aligned base guarantee); ws 7 forward
+ * and ws 14: mma.sync kernels (ESVIT_ATTN_TC selects). */
 int esvit_window_attn_expand_bias(const float* bias_table, float* bias_ws, int nH, int ws, void* stream);
 int esvit_window_attn_fwd(const void* qkv, const void* qkv_bias, const float* bias_table, float* bias_ws, int bias_ready,
                           void* out, float* lse, int B, int H, int W, int C, int nH, int ws, int shift, float scale,
